@@ -1,0 +1,979 @@
+// C ABI of the B200-native C2-Ray hot path: handle, module-state marshalling, the evolve3D outer
+// loop (evolve.F90:83-281), pass_all_sources (evolve.F90:444-495 + master_slave.F90:74-96),
+// global_pass (evolve.F90:499-573), the photon statistics bookkeeping (photonstatistics.F90) and
+// the rank reduction (evolve.F90:577-616) over NCCL.  See include/c2ray_b200.h.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "c2b_common.cuh"
+
+using namespace c2b;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) {
+      err = std::string("cannot load NCCL: ") + dlerror();
+      return false;
+    }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString) {
+      err = "NCCL library lacks a required symbol";
+      return false;
+    }
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct c2b_handle {
+  c2b_config cfg;
+  size_t ncell = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string error;
+  // grids
+  float* d_ndens = nullptr;
+  double *d_xh = nullptr, *d_xh_av = nullptr, *d_xh_intermed = nullptr, *d_phih = nullptr;
+  float *d_clump = nullptr, *d_lls = nullptr, *d_f32tmp = nullptr;
+  double *d_thick = nullptr, *d_thin = nullptr;
+  bool have_tables = false, have_density = false, have_xh = false, have_geometry = false;
+  // sources
+  int NumSrc = 0, nwork = 0;
+  int* d_srcpos = nullptr;
+  double* d_normflux = nullptr;
+  int* d_work = nullptr;
+  int* d_nbox = nullptr;
+  double* d_loss = nullptr;
+  int* h_nbox = nullptr;      // pinned
+  double* h_loss = nullptr;   // pinned
+  std::vector<int> work;      // 0-based source indices of this rank
+  std::vector<int> srcpos;
+  double sum_normflux = 0.0, S_star = 0.0;
+  // ray-trace launch resources
+  unsigned int* d_ticket = nullptr;
+  double* d_scratch = nullptr;
+  int rt_grid = 0, plane_stride = 0;
+  int lim[3][2];
+  // reductions
+  double* d_partials = nullptr;
+  double* d_stats = nullptr;
+  double* h_stats = nullptr;  // pinned, kNumStat
+  double* d_small = nullptr;  // 4 doubles for the packed scalar all-reduce
+  double* h_small = nullptr;  // pinned
+  int chem_blocks = 0;
+  // module state
+  double dr[3] = {0, 0, 0}, vol = 0.0;
+  float clumping = 1.0f;
+  double coldensh_LLS = 0.0, R_max_LLS = 0.0, temper_val = 1.0e4;
+  double h0_before = 0, h1_before = 0, h0_after = 0, h1_after = 0, totrec = 0, totcoll = 0, dh0 = 0,
+         total_ion = 0;
+  double photon_loss = 0.0, LLS_loss = 0.0, grtotal_ion = 0.0, grtotal_src = 0.0;
+  double sum_xh_intermed = 0.0;
+  // restart state
+  int iter_niter = 0;
+  double iter_photon_loss_all = 0.0;
+  bool have_iter_state = false;
+  // NCCL
+  ncclComm_t comm = nullptr;
+  long long launches = 0;
+};
+
+#define C2B_CHECK_H(h)            \
+  do {                            \
+    if (!(h)) return 100;         \
+  } while (0)
+
+#define CU(h, call)                                                                     \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      char buf__[512];                                                                  \
+      snprintf(buf__, sizeof(buf__), "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e__));                                                \
+      (h)->error = buf__;                                                               \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define NC(h, call)                                                                     \
+  do {                                                                                  \
+    ncclResult_t r__ = (call);                                                          \
+    if (r__ != ncclSuccess) {                                                           \
+      char buf__[512];                                                                  \
+      snprintf(buf__, sizeof(buf__), "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+               g_nccl.GetErrorString(r__));                                             \
+      (h)->error = buf__;                                                               \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+static int fail(c2b_handle* h, const char* msg) {
+  h->error = msg;
+  return 3;
+}
+
+static int bind_device(c2b_handle* h) {
+  CU(h, cudaSetDevice(h->cfg.device));
+  return 0;
+}
+
+extern "C" {
+
+int c2b_default_config(c2b_config* c) {
+  if (!c) return 100;
+  memset(c, 0, sizeof(*c));
+  c->mesh[0] = c->mesh[1] = c->mesh[2] = 300;              // sizes.f90:33
+  c->device = 0;
+  c->rank = 0;
+  c->nranks = 1;
+  c->isothermal = 1;                                       // c2ray_parameters.f90:28
+  c->type_of_clumping = 1;                                 // :75
+  c->use_LLS = 1;                                          // :80
+  c->type_of_LLS = 1;                                      // :87
+  c->subboxsize = 5;                                       // :54
+  c->max_subbox = 1000;                                    // :61
+  c->max_outer_iter = 100;                                 // evolve.F90:228
+  c->epsilon = 1e-14;                                      // :31
+  c->convergence_fraction = (double)1.0e-4f;               // :25 (default-real literal)
+  c->minimum_fractional_change = (double)1.0e-3f;          // :34
+  c->minimum_fraction_of_atoms = (double)1.0e-8f;          // :40
+  c->loss_fraction = 1e-2;                                 // :67
+  c->max_coldensh = (double)2e19f;                         // evolve_point.F90:95
+  c->tau_photo_limit = (double)1.0e-7f;                    // radiation_photoionrates.F90:244
+  c->minlogtau = -20.0;                                    // radiation_tables.F90:45
+  c->dlogtau = (4.0 - (-20.0)) / (double)(float)C2B_NUMTAU;  // :47
+  c->sigma_HI = 1.0 * (double)6.30e-18f;                   // cgsphotoconstants.f90:24
+  c->pi = (double)3.141592654f;                            // mathconstants.f90:21
+  c->sqrt2 = (double)sqrtf(2.0f);                          // column_density.f90:53
+  c->sqrt3 = (double)sqrtf(3.0f);                          // :52
+  c->bh00 = 2.59e-13;                                      // cgsconstants.f90:66
+  c->albpow = -0.7;                                        // :64
+  const double eth0 = (double)13.598f;                     // :76
+  const double ev2k = (double)(1.0f / 8.617e-05f);         // :39
+  c->temph0 = eth0 * ev2k;                                 // :80
+  c->colh0 = (double)1.3e-8f * (double)0.83f * (double)1.0f / (eth0 * eth0);  // :86
+  c->abu_c = (double)7.1e-7f;                              // abundances.f90:26
+  return 0;
+}
+
+int c2b_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* c2b_last_error(const c2b_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int c2b_create(const c2b_config* cfg, c2b_handle** out) {
+  if (!cfg || !out) {
+    g_create_error = "c2b_create: null argument";
+    return 100;
+  }
+  *out = nullptr;
+  for (int d = 0; d < 3; ++d)
+    if (cfg->mesh[d] < 4 || cfg->mesh[d] > 4096) {
+      g_create_error = "c2b_create: mesh must be within [4, 4096] per axis";
+      return 101;
+    }
+  if (!cfg->isothermal) {
+    g_create_error = "c2b_create: only isothermal=.true. is implemented (thermal.f90 needs tables/corocool.tab, absent from the reference)";
+    return 102;
+  }
+  if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) {
+    g_create_error = "c2b_create: bad rank/nranks";
+    return 103;
+  }
+  if (cfg->use_LLS && (cfg->type_of_LLS < 1 || cfg->type_of_LLS > 3)) {
+    g_create_error = "c2b_create: type_of_LLS must be 1, 2 or 3";
+    return 104;
+  }
+  if (cfg->type_of_clumping < 1 || cfg->type_of_clumping > 5 || cfg->subboxsize < 1 || cfg->max_subbox < 1) {
+    g_create_error = "c2b_create: bad type_of_clumping / subboxsize / max_subbox";
+    return 105;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1) {
+    g_create_error = std::string("c2b_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); this library has no CPU fallback";
+    return 110;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = "c2b_create: device ordinal out of range";
+    return 111;
+  }
+  c2b_handle* h = new c2b_handle();
+  h->cfg = *cfg;
+  h->ncell = (size_t)cfg->mesh[0] * cfg->mesh[1] * cfg->mesh[2];
+  auto bail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string("c2b_create: ") + what + ": " + cudaGetErrorString(ce);
+    c2b_destroy(h);
+    return 112;
+  };
+  if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  for (auto& ev : h->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  const size_t n = h->ncell;
+  if ((e = cudaMalloc(&h->d_ndens, n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc ndens", e);
+  if ((e = cudaMalloc(&h->d_xh, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc xh", e);
+  if ((e = cudaMalloc(&h->d_xh_av, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc xh_av", e);
+  if ((e = cudaMalloc(&h->d_xh_intermed, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc xh_intermed", e);
+  if ((e = cudaMalloc(&h->d_phih, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phih", e);
+  if ((e = cudaMemsetAsync(h->d_phih, 0, n * sizeof(double), h->stream)) != cudaSuccess) return bail("memset", e);
+  if ((e = cudaMalloc(&h->d_thick, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_ticket, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+  // evolve_source.F90:100-102 (periodic_bc)
+  int smax = 0;
+  for (int d = 0; d < 3; ++d) {
+    h->lim[d][1] = std::min(cfg->max_subbox, cfg->mesh[d] / 2 - 1 + cfg->mesh[d] % 2);
+    h->lim[d][0] = std::min(cfg->max_subbox, cfg->mesh[d] / 2);
+    smax = std::max(smax, std::max(h->lim[d][0], h->lim[d][1]));
+  }
+  h->plane_stride = smax + 1;
+  h->rt_grid = raytrace_max_grid();
+  const size_t scratch = raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt_grid;
+  if ((e = cudaMalloc(&h->d_scratch, scratch * sizeof(double))) != cudaSuccess) return bail("cudaMalloc scratch", e);
+  h->chem_blocks = chemistry_blocks();
+  if ((e = cudaMalloc(&h->d_partials, (size_t)h->chem_blocks * kNumStat * sizeof(double))) != cudaSuccess)
+    return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_stats, kNumStat * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&h->h_stats, kNumStat * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&h->h_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("sync", e);
+  *out = h;
+  return 0;
+}
+
+void c2b_destroy(c2b_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
+  cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
+  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
+  cudaFree(h->d_work); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
+  cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
+  if (h->h_nbox) cudaFreeHost(h->h_nbox);
+  if (h->h_loss) cudaFreeHost(h->h_loss);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->h_small) cudaFreeHost(h->h_small);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+int c2b_get_unique_id(void* id) {
+  if (!id) return 100;
+  std::string err;
+  if (!g_nccl.load(err)) {
+    g_create_error = err;
+    return 2;
+  }
+  static_assert(sizeof(ncclUniqueId) <= C2B_UNIQUE_ID_BYTES, "unique id size");
+  ncclUniqueId uid;
+  if (g_nccl.GetUniqueId(&uid) != ncclSuccess) {
+    g_create_error = "ncclGetUniqueId failed";
+    return 2;
+  }
+  memset(id, 0, C2B_UNIQUE_ID_BYTES);
+  memcpy(id, &uid, sizeof(uid));
+  return 0;
+}
+
+int c2b_comm_init(c2b_handle* h, const void* id) {
+  C2B_CHECK_H(h);
+  if (!id) return fail(h, "c2b_comm_init: null id");
+  if (h->cfg.nranks == 1) return 0;
+  if (!g_nccl.load(h->error)) return 2;
+  if (bind_device(h)) return 1;
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NC(h, g_nccl.CommInitRank(&h->comm, h->cfg.nranks, uid, h->cfg.rank));
+  return 0;
+}
+
+// ---- inputs -------------------------------------------------------------------------------------
+int c2b_set_tables(c2b_handle* h, const double* thick, const double* thin, int32_t n) {
+  C2B_CHECK_H(h);
+  if (!thick || !thin) return fail(h, "c2b_set_tables: null table");
+  if (n != kTableLen) return fail(h, "c2b_set_tables: n must be NumTau+1 = 2001");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_thick, thick, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_thin, thin, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_tables = true;
+  return 0;
+}
+
+int c2b_rad_ini_blackbody(c2b_handle* h, double T_eff, double S_star, double freq_min, double freq_max,
+                          double hplanck, double k_B, double two_pi_over_c_square, double R_solar,
+                          double pl_index_cross_section, double* thick_out, double* thin_out) {
+  C2B_CHECK_H(h);
+  if (bind_device(h)) return 1;
+  SedParams sp;
+  sp.T_eff = T_eff; sp.S_star = S_star; sp.freq_min = freq_min; sp.freq_max = freq_max;
+  sp.hplanck = hplanck; sp.k_B = k_B; sp.two_pi_over_c_square = two_pi_over_c_square;
+  sp.R_solar = R_solar; sp.pi = h->cfg.pi; sp.pl_index_cross_section = pl_index_cross_section;
+  sp.minlogtau = h->cfg.minlogtau; sp.dlogtau = h->cfg.dlogtau;
+  int rc = build_blackbody_tables(sp, h->d_thick, h->d_thin, h->stream, nullptr);
+  h->launches += 1;
+  if (rc) return fail(h, "c2b_rad_ini_blackbody: table kernel failed");
+  h->have_tables = true;
+  if (thick_out) CU(h, cudaMemcpy(thick_out, h->d_thick, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
+  if (thin_out) CU(h, cudaMemcpy(thin_out, h->d_thin, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int c2b_set_density(c2b_handle* h, const float* ndens) {
+  C2B_CHECK_H(h);
+  if (!ndens) return fail(h, "c2b_set_density: null pointer");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_ndens, ndens, h->ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_density = true;
+  return 0;
+}
+
+int c2b_set_geometry(c2b_handle* h, const double dr[3], double vol) {
+  C2B_CHECK_H(h);
+  if (!dr) return fail(h, "c2b_set_geometry: null pointer");
+  if (!(dr[0] > 0) || !(dr[1] > 0) || !(dr[2] > 0) || !(vol > 0)) return fail(h, "c2b_set_geometry: non-positive dr/vol");
+  h->dr[0] = dr[0]; h->dr[1] = dr[1]; h->dr[2] = dr[2];
+  h->vol = vol;
+  h->have_geometry = true;
+  return 0;
+}
+
+int c2b_cosmo_evol(c2b_handle* h, double zfactor) {
+  C2B_CHECK_H(h);
+  if (!(zfactor > 0)) return fail(h, "c2b_cosmo_evol: zfactor must be positive");
+  if (!h->have_density || !h->have_geometry) return fail(h, "c2b_cosmo_evol: density/geometry not set");
+  if (bind_device(h)) return 1;
+  const double zfactor3 = zfactor * zfactor * zfactor;  // cosmology.F90:174
+  for (int d = 0; d < 3; ++d) h->dr[d] = h->dr[d] * zfactor;
+  h->vol = h->vol * zfactor3;
+  launch_scale_density(h->d_ndens, h->ncell, zfactor3, h->stream);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+int c2b_set_clumping_scalar(c2b_handle* h, float clumping) {
+  C2B_CHECK_H(h);
+  h->clumping = clumping;
+  return 0;
+}
+
+static int upload_f32_grid(c2b_handle* h, float** dst, const float* src) {
+  if (bind_device(h)) return 1;
+  if (!*dst) CU(h, cudaMalloc(dst, h->ncell * sizeof(float)));
+  CU(h, cudaMemcpyAsync(*dst, src, h->ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int c2b_set_clumping_grid(c2b_handle* h, const float* g) {
+  C2B_CHECK_H(h);
+  if (!g) return fail(h, "c2b_set_clumping_grid: null pointer");
+  if (h->cfg.type_of_clumping < 3) return fail(h, "c2b_set_clumping_grid: type_of_clumping is 1 or 2 (scalar)");
+  return upload_f32_grid(h, &h->d_clump, g);
+}
+
+int c2b_set_lls_scalar(c2b_handle* h, double v) {
+  C2B_CHECK_H(h);
+  h->coldensh_LLS = v;
+  return 0;
+}
+int c2b_set_lls_grid(c2b_handle* h, const float* g) {
+  C2B_CHECK_H(h);
+  if (!g) return fail(h, "c2b_set_lls_grid: null pointer");
+  if (h->cfg.type_of_LLS != 2) return fail(h, "c2b_set_lls_grid: type_of_LLS is not 2");
+  return upload_f32_grid(h, &h->d_lls, g);
+}
+int c2b_set_lls_rmax(c2b_handle* h, double v) {
+  C2B_CHECK_H(h);
+  h->R_max_LLS = v;
+  return 0;
+}
+int c2b_set_temperature(c2b_handle* h, double t) {
+  C2B_CHECK_H(h);
+  if (!(t > 0)) return fail(h, "c2b_set_temperature: temperature must be positive");
+  h->temper_val = t;
+  return 0;
+}
+
+int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const double* nf, double S_star) {
+  C2B_CHECK_H(h);
+  if (NumSrc < 0) return fail(h, "c2b_set_sources: negative NumSrc");
+  if (NumSrc > 0 && (!srcpos || !nf)) return fail(h, "c2b_set_sources: null pointer");
+  for (int s = 0; s < NumSrc; ++s)
+    for (int d = 0; d < 3; ++d)
+      if (srcpos[3 * s + d] < 1 || srcpos[3 * s + d] > h->cfg.mesh[d])
+        return fail(h, "c2b_set_sources: source position outside the mesh (positions are 1-based)");
+  if (bind_device(h)) return 1;
+  cudaFree(h->d_srcpos); cudaFree(h->d_normflux); cudaFree(h->d_work); cudaFree(h->d_nbox); cudaFree(h->d_loss);
+  h->d_srcpos = nullptr; h->d_normflux = nullptr; h->d_work = nullptr; h->d_nbox = nullptr; h->d_loss = nullptr;
+  if (h->h_nbox) cudaFreeHost(h->h_nbox);
+  if (h->h_loss) cudaFreeHost(h->h_loss);
+  h->h_nbox = nullptr; h->h_loss = nullptr;
+  h->NumSrc = NumSrc;
+  h->S_star = S_star;
+  h->work.clear();
+  h->srcpos.assign(srcpos, srcpos + 3 * (size_t)NumSrc);
+  // do ns1=1+rank,NumSrc,npr (master_slave.F90:85)
+  for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
+  h->nwork = (int)h->work.size();
+  h->sum_normflux = 0.0;
+  for (int s = 0; s < NumSrc; ++s) h->sum_normflux = h->sum_normflux + nf[s];  // sum(NormFlux_stellar(1:NumSrc))
+  if (NumSrc == 0) return 0;
+  const size_t ns = (size_t)NumSrc;
+  CU(h, cudaMalloc(&h->d_srcpos, 3 * ns * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_normflux, ns * sizeof(double)));
+  CU(h, cudaMalloc(&h->d_work, std::max<size_t>(1, h->work.size()) * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_nbox, ns * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_loss, ns * sizeof(double)));
+  CU(h, cudaMallocHost(&h->h_nbox, ns * sizeof(int)));
+  CU(h, cudaMallocHost(&h->h_loss, ns * sizeof(double)));
+  CU(h, cudaMemcpyAsync(h->d_srcpos, srcpos, 3 * ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_normflux, nf, ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (!h->work.empty())
+    CU(h, cudaMemcpyAsync(h->d_work, h->work.data(), h->work.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->d_nbox, 0, ns * sizeof(int), h->stream));
+  CU(h, cudaMemsetAsync(h->d_loss, 0, ns * sizeof(double), h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  memset(h->h_nbox, 0, ns * sizeof(int));
+  memset(h->h_loss, 0, ns * sizeof(double));
+  return 0;
+}
+
+int c2b_set_xh(c2b_handle* h, const double* xh) {
+  C2B_CHECK_H(h);
+  if (!xh) return fail(h, "c2b_set_xh: null pointer");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_xh, xh, h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_xh = true;
+  return 0;
+}
+
+// ---- internals of the hot path ------------------------------------------------------------------
+static void fill_chem(c2b_handle* h, double dt, ChemParams& cp) {
+  const c2b_config& c = h->cfg;
+  cp.ncell = h->ncell;
+  cp.ndens = h->d_ndens;
+  cp.xh = h->d_xh;
+  cp.xh_av = h->d_xh_av;
+  cp.xh_intermed = h->d_xh_intermed;
+  cp.phih = h->d_phih;
+  cp.clumping_grid = (c.type_of_clumping >= 3) ? h->d_clump : nullptr;
+  cp.clumping = h->clumping;
+  cp.dt = dt;
+  const double T = h->temper_val;
+  cp.bh00 = c.bh00;
+  cp.powT = std::pow(T / (double)1e4f, c.albpow);   // (temp0/1e4)**albpow, doric.f90:74
+  cp.bh00_powT = c.bh00 * cp.powT;
+  cp.sqrtT = std::sqrt(T);
+  cp.expT = std::exp(-c.temph0 / T);
+  cp.colh0 = c.colh0;
+  cp.acolh0 = c.colh0 * cp.sqrtT * cp.expT;         // doric.f90:77
+  cp.abu_c = c.abu_c;
+  cp.epsilon = c.epsilon;
+  cp.minimum_fractional_change = c.minimum_fractional_change;
+  cp.minimum_fraction_of_atoms = c.minimum_fraction_of_atoms;
+  cp.partials = h->d_partials;
+}
+
+static int fetch_stats(c2b_handle* h) {
+  launch_finalize_partials(h->d_partials, h->chem_blocks, h->d_stats, h->stream);
+  h->launches += 1;
+  CU(h, cudaMemcpyAsync(h->h_stats, h->d_stats, kNumStat * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+static int check_ready(c2b_handle* h) {
+  if (!h->have_tables) return fail(h, "photo-ionization tables not set (c2b_set_tables / c2b_rad_ini_blackbody)");
+  if (!h->have_density) return fail(h, "density not set (c2b_set_density)");
+  if (!h->have_geometry) return fail(h, "geometry not set (c2b_set_geometry)");
+  if (!h->have_xh) return fail(h, "ionization fractions not set (c2b_set_xh)");
+  if (h->cfg.type_of_clumping >= 3 && !h->d_clump) return fail(h, "clumping grid not set");
+  if (h->cfg.use_LLS && h->cfg.type_of_LLS == 2 && !h->d_lls) return fail(h, "LLS grid not set");
+  if (h->cfg.nranks > 1 && !h->comm) return fail(h, "nranks > 1 but c2b_comm_init was not called");
+  return 0;
+}
+
+static void fill_photon_stats(const c2b_handle* h, double dt, c2b_photon_stats* st) {
+  st->h0_before = h->h0_before; st->h1_before = h->h1_before;
+  st->h0_after = h->h0_after; st->h1_after = h->h1_after;
+  st->totrec = h->totrec; st->totcollisions = h->totcoll;
+  st->dh0 = h->dh0; st->total_ion = h->total_ion;
+  // report_photonstatistics, photonstatistics.F90:254-281
+  st->total_photon_loss = h->photon_loss * dt * (double)(float)h->cfg.mesh[0] * (double)(float)h->cfg.mesh[1] *
+                          (double)(float)h->cfg.mesh[2];
+  st->LLS_loss = h->LLS_loss;
+  st->totalsrc = h->sum_normflux * h->S_star * dt;
+  st->photcons = (h->total_ion + h->LLS_loss - h->totcoll) / st->totalsrc;
+}
+
+// after a statistics reduction over (x_l, x_r): state_after + total_rates + total_ionizations
+static void absorb_after(c2b_handle* h, double dt) {
+  h->h0_after = h->h_stats[kH0] * h->vol;
+  h->h1_after = h->h_stats[kH1] * h->vol;
+  h->totrec = h->h_stats[kRec] * h->vol * dt;
+  h->totcoll = h->h_stats[kColl] * h->vol * dt;
+  h->dh0 = (h->h0_before - h->h0_after);
+  h->total_ion = h->totrec + h->dh0;
+}
+
+static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* coldens_dbg, float* ms) {
+  const c2b_config& c = h->cfg;
+  RtParams rp;
+  memset(&rp, 0, sizeof(rp));
+  for (int d = 0; d < 3; ++d) {
+    rp.n[d] = c.mesh[d];
+    rp.lim[d][0] = h->lim[d][0];
+    rp.lim[d][1] = h->lim[d][1];
+    rp.dr[d] = h->dr[d];
+  }
+  rp.subboxsize = c.subboxsize;
+  rp.plane_stride = h->plane_stride;
+  rp.ndens = h->d_ndens;
+  rp.xh_av = h->d_xh_av;
+  rp.phih = h->d_phih;
+  rp.lls_grid = h->d_lls;
+  rp.thick = h->d_thick;
+  rp.thin = h->d_thin;
+  rp.srcpos = h->d_srcpos;
+  rp.normflux = h->d_normflux;
+  rp.work = d_work;
+  rp.nwork = nwork;
+  rp.ticket = h->d_ticket;
+  rp.scratch = h->d_scratch;
+  rp.nbox_out = h->d_nbox;
+  rp.loss_out = h->d_loss;
+  rp.coldens_dbg = coldens_dbg;
+  rp.S_star = h->S_star;
+  rp.vol = h->vol;
+  rp.use_lls = c.use_LLS;
+  rp.type_lls = c.type_of_LLS;
+  rp.coldensh_lls = h->coldensh_LLS;
+  rp.rmax_lls2 = h->R_max_LLS * h->R_max_LLS;
+  rp.sigma_HI = c.sigma_HI;
+  rp.max_coldensh = c.max_coldensh;
+  rp.tau_photo_limit = c.tau_photo_limit;
+  rp.minlogtau = c.minlogtau;
+  rp.dlogtau = c.dlogtau;
+  rp.loss_fraction = c.loss_fraction;
+  rp.epsilon = c.epsilon;
+  rp.pi = c.pi;
+  rp.sqrt2 = c.sqrt2;
+  rp.sqrt3 = c.sqrt3;
+  CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+  CU(h, cudaEventRecord(h->ev[0], h->stream));
+  if (nwork > 0) {
+    const int grid = std::min(h->rt_grid, nwork);
+    launch_raytrace(rp, grid, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+  }
+  CU(h, cudaEventRecord(h->ev[1], h->stream));
+  if (ms) {
+    CU(h, cudaEventSynchronize(h->ev[1]));
+    CU(h, cudaEventElapsedTime(ms, h->ev[0], h->ev[1]));
+  }
+  return 0;
+}
+
+static int64_t box_updates(const c2b_handle* h, int nbox) {
+  if (nbox <= 0) return 0;
+  int64_t u = 1;
+  for (int d = 0; d < 3; ++d) {
+    const int r = std::min(h->cfg.subboxsize * nbox, h->lim[d][1]);
+    const int l = std::min(h->cfg.subboxsize * nbox, h->lim[d][0]);
+    u *= (int64_t)(r + l + 1);
+  }
+  return u;
+}
+
+int c2b_begin_step(c2b_handle* h, double* sum_xh) {
+  C2B_CHECK_H(h);
+  if (int rc = check_ready(h)) return rc;
+  if (bind_device(h)) return 1;
+  ChemParams cp;
+  fill_chem(h, 0.0, cp);
+  // state_before(xh), photonstatistics.F90:104-132 (+ sum(xh) for evolve.F90:183)
+  launch_stats(cp, h->d_xh, nullptr, h->chem_blocks, h->stream);
+  h->launches += 1;
+  if (int rc = fetch_stats(h)) return rc;
+  h->h0_before = h->h_stats[kH0] * h->vol;
+  h->h1_before = h->h_stats[kH1] * h->vol;
+  h->sum_xh_intermed = h->h_stats[kSumXh];
+  if (sum_xh) *sum_xh = h->sum_xh_intermed;
+  // xh_av=xh ; xh_intermed=xh  (evolve.F90:140-147)
+  CU(h, cudaMemcpyAsync(h->d_xh_av, h->d_xh, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_xh_intermed, h->d_xh, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
+}
+
+int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_report* rep) {
+  C2B_CHECK_H(h);
+  (void)niter;
+  (void)dt;
+  if (int rc = check_ready(h)) return rc;
+  if (bind_device(h)) return 1;
+  // set_rates_to_zero, evolve.F90:430-440
+  CU(h, cudaMemsetAsync(h->d_phih, 0, h->ncell * sizeof(double), h->stream));
+  h->photon_loss = 0.0;
+  h->LLS_loss = 0.0;
+  float ms_rt = 0.f, ms_ar = 0.f;
+  double loss_sum = 0.0, nbox_sum = 0.0, upd_sum = 0.0;
+  if (h->NumSrc > 0) {
+    CU(h, cudaMemsetAsync(h->d_nbox, 0, (size_t)h->NumSrc * sizeof(int), h->stream));
+    CU(h, cudaMemsetAsync(h->d_loss, 0, (size_t)h->NumSrc * sizeof(double), h->stream));
+    if (int rc = trace_sources(h, h->d_work, h->nwork, nullptr, &ms_rt)) return rc;
+    CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // photon_loss(1)=photon_loss(1)+photon_loss_src ; sum_nbox=sum_nbox+nbox, in source order
+    for (int w : h->work) {
+      loss_sum = loss_sum + h->h_loss[w];
+      nbox_sum += (double)h->h_nbox[w];
+      upd_sum += (double)box_updates(h, h->h_nbox[w]);
+    }
+  }
+  if (h->cfg.nranks > 1) {
+    // mpi_accumulate_grid_quantities, evolve.F90:577-616
+    CU(h, cudaEventRecord(h->ev[2], h->stream));
+    h->h_small[0] = loss_sum; h->h_small[1] = nbox_sum; h->h_small[2] = upd_sum; h->h_small[3] = 0.0;
+    CU(h, cudaMemcpyAsync(h->d_small, h->h_small, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    NC(h, g_nccl.AllReduce(h->d_phih, h->d_phih, h->ncell, ncclDouble, ncclSum, h->comm, h->stream));
+    NC(h, g_nccl.AllReduce(h->d_small, h->d_small, 4, ncclDouble, ncclSum, h->comm, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_small, h->d_small, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaEventRecord(h->ev[3], h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventElapsedTime(&ms_ar, h->ev[2], h->ev[3]));
+    loss_sum = h->h_small[0]; nbox_sum = h->h_small[1]; upd_sum = h->h_small[2];
+  }
+  h->photon_loss = loss_sum;
+  h->iter_photon_loss_all = loss_sum;
+  if (rep) {
+    rep->photon_loss_all = loss_sum;
+    rep->sum_nbox_all = (int64_t)llround(nbox_sum);
+    rep->updates = (int64_t)llround(upd_sum);
+    rep->ms_raytrace = ms_rt;
+    rep->ms_allreduce = ms_ar;
+  }
+  return 0;
+}
+
+int c2b_global_pass(c2b_handle* h, double dt, c2b_global_report* rep) {
+  C2B_CHECK_H(h);
+  if (int rc = check_ready(h)) return rc;
+  if (bind_device(h)) return 1;
+  // photon_loss(:)=photon_loss_all(:)/(real(mesh(1))*real(mesh(2))*real(mesh(3))), evolve.F90:525
+  const float m = (float)h->cfg.mesh[0] * (float)h->cfg.mesh[1] * (float)h->cfg.mesh[2];
+  h->photon_loss = h->iter_photon_loss_all / (double)m;
+  ChemParams cp;
+  fill_chem(h, dt, cp);
+  CU(h, cudaEventRecord(h->ev[0], h->stream));
+  launch_chemistry(cp, h->chem_blocks, h->stream);
+  h->launches += 1;
+  CU(h, cudaEventRecord(h->ev[1], h->stream));
+  if (int rc = fetch_stats(h)) return rc;
+  float ms = 0.f;
+  CU(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+  absorb_after(h, dt);  // calculate_photon_statistics(dt,xh_intermed,xh_av), evolve.F90:570
+  h->sum_xh_intermed = h->h_stats[kSumXh];
+  if (rep) {
+    rep->conv_flag = (int32_t)llround(h->h_stats[kConv]);
+    rep->min_avg_neutral = 1.0 - h->h_stats[kMaxXhAv];
+    rep->sum_xh_intermed = h->sum_xh_intermed;
+    fill_photon_stats(h, dt, &rep->stats);
+    rep->ms_chemistry = ms;
+  }
+  return 0;
+}
+
+int c2b_end_step(c2b_handle* h, double dt, int32_t converged, c2b_photon_stats* final_stats) {
+  C2B_CHECK_H(h);
+  if (int rc = check_ready(h)) return rc;
+  if (bind_device(h)) return 1;
+  if (converged)  // xh(:,:,:)=xh_intermed(:,:,:), evolve.F90:215-217
+    CU(h, cudaMemcpyAsync(h->d_xh, h->d_xh_intermed, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  // calculate_photon_statistics(dt,xh,xh_av), evolve.F90:277
+  ChemParams cp;
+  fill_chem(h, dt, cp);
+  launch_stats(cp, h->d_xh, h->d_xh_av, h->chem_blocks, h->stream);
+  h->launches += 1;
+  if (int rc = fetch_stats(h)) return rc;
+  absorb_after(h, dt);
+  if (final_stats) fill_photon_stats(h, dt, final_stats);
+  // update_grandtotal_photonstatistics, photonstatistics.F90:286-293
+  h->grtotal_src = h->grtotal_src + h->sum_normflux * h->S_star * dt;
+  h->grtotal_ion = h->grtotal_ion + h->total_ion - h->totcoll;
+  return 0;
+}
+
+int c2b_evolve3d(c2b_handle* h, double time, double dt, int32_t restart, c2b_step_report* rep) {
+  C2B_CHECK_H(h);
+  (void)time;
+  if (!rep) return fail(h, "c2b_evolve3d: null report");
+  if (!(dt > 0)) return fail(h, "c2b_evolve3d: dt must be positive");
+  memset(rep, 0, sizeof(*rep));
+  const c2b_config& c = h->cfg;
+  const long long launches0 = h->launches;
+  if (bind_device(h)) return 1;
+  cudaEvent_t t0, t1;
+  CU(h, cudaEventCreate(&t0));
+  CU(h, cudaEventCreate(&t1));
+  CU(h, cudaEventRecord(t0, h->stream));
+  int niter = 0;
+  int conv_flag = c.mesh[0] * c.mesh[1] * c.mesh[2];
+  // prev_sum_xh1_int=2.0*mesh(1)*mesh(2)*mesh(3): default-real arithmetic (evolve.F90:150-151)
+  double prev_sum_xh1 = (double)(2.0f * (float)c.mesh[0] * (float)c.mesh[1] * (float)c.mesh[2]);
+  double prev_sum_xh0 = prev_sum_xh1;
+  double sum_xh1 = 0.0;
+  int rc = 0;
+  if (restart == 0) {
+    rc = c2b_begin_step(h, &sum_xh1);
+  } else {
+    // start_from_dump + global_pass (evolve.F90:154-158); state_before still runs first (:136)
+    if (!h->have_iter_state) rc = fail(h, "c2b_evolve3d: restart requested but c2b_set_iter_state was not called");
+    if (!rc) {
+      ChemParams cp;
+      fill_chem(h, 0.0, cp);
+      launch_stats(cp, h->d_xh, nullptr, h->chem_blocks, h->stream);
+      h->launches += 1;
+      rc = fetch_stats(h);
+    }
+    if (!rc) {
+      h->h0_before = h->h_stats[kH0] * h->vol;
+      h->h1_before = h->h_stats[kH1] * h->vol;
+      niter = h->iter_niter;
+      c2b_global_report gr;
+      rc = c2b_global_pass(h, dt, &gr);
+      conv_flag = gr.conv_flag;
+      sum_xh1 = gr.sum_xh_intermed;
+      rep->ms_chemistry += gr.ms_chemistry;
+    }
+  }
+  if (rc) return rc;
+  // conv_criterion=min(int(convergence_fraction*mesh(1)*mesh(2)*mesh(3)),(NumSrc-1)/3), evolve.F90:162
+  const int c1 = (int)(c.convergence_fraction * (double)c.mesh[0] * (double)c.mesh[1] * (double)c.mesh[2]);
+  const int c2 = (h->NumSrc - 1) / 3;
+  const int conv_criterion = std::min(c1, c2);
+  rep->conv_criterion = conv_criterion;
+  int converged = 0;
+  for (;;) {
+    // sum_xh1_int=sum(xh_intermed) ; sum_xh0_int=real(N^3)-sum_xh1_int  (evolve.F90:183-196)
+    const double sum_xh0 = (double)(float)(c.mesh[0] * c.mesh[1] * c.mesh[2]) - sum_xh1;
+    const double rel1 = (sum_xh1 > 0.0) ? std::fabs(sum_xh1 - prev_sum_xh1) / sum_xh1 : 1.0;
+    const double rel0 = (sum_xh0 > 0.0) ? std::fabs(sum_xh0 - prev_sum_xh0) / sum_xh0 : 1.0;
+    if (niter < C2B_MAX_ITER) {
+      rep->rel_change_sum_xh1[niter] = rel1;
+      rep->rel_change_sum_xh0[niter] = rel0;
+    }
+    if (conv_flag < conv_criterion || (rel1 < c.convergence_fraction && rel0 < c.convergence_fraction)) {
+      converged = 1;  // "Multiple sources convergence reached", :212-226
+      break;
+    } else if (niter > c.max_outer_iter) {
+      converged = 0;  // 'Multiple sources not converging', :228-232
+      break;
+    }
+    prev_sum_xh1 = sum_xh1;
+    prev_sum_xh0 = sum_xh0;
+    niter += 1;
+    c2b_pass_report pr;
+    if ((rc = c2b_pass_all_sources(h, niter, dt, &pr))) return rc;
+    c2b_global_report gr;
+    if ((rc = c2b_global_pass(h, dt, &gr))) return rc;
+    conv_flag = gr.conv_flag;
+    sum_xh1 = gr.sum_xh_intermed;
+    h->iter_niter = niter;
+    rep->ms_raytrace += pr.ms_raytrace;
+    rep->ms_allreduce += pr.ms_allreduce;
+    rep->ms_chemistry += gr.ms_chemistry;
+    rep->total_updates += pr.updates;
+    if (niter < C2B_MAX_ITER) {
+      rep->conv_flag[niter] = conv_flag;
+      rep->photon_loss_all[niter] = pr.photon_loss_all;
+      rep->sum_nbox_all[niter] = pr.sum_nbox_all;
+      rep->updates[niter] = pr.updates;
+      rep->iter_stats[niter] = gr.stats;
+    }
+  }
+  rep->niter = niter;
+  rep->converged = converged;
+  if ((rc = c2b_end_step(h, dt, converged, &rep->final_stats))) return rc;
+  rep->grtotal_ion = h->grtotal_ion;
+  rep->grtotal_src = h->grtotal_src;
+  h->have_iter_state = false;
+  CU(h, cudaEventRecord(t1, h->stream));
+  CU(h, cudaEventSynchronize(t1));
+  float ms = 0.f;
+  CU(h, cudaEventElapsedTime(&ms, t0, t1));
+  rep->ms_total = ms;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  rep->kernel_launches = h->launches - launches0;
+  return 0;
+}
+
+// ---- outputs -------------------------------------------------------------------------------------
+static int download(c2b_handle* h, void* dst, const void* src, size_t bytes, const char* what) {
+  if (!dst) {
+    h->error = std::string(what) + ": null pointer";
+    return 3;
+  }
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+int c2b_get_xh(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_xh, h->ncell * 8, "c2b_get_xh"); }
+int c2b_get_xh_av(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_xh_av, h->ncell * 8, "c2b_get_xh_av"); }
+int c2b_get_xh_intermed(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_xh_intermed, h->ncell * 8, "c2b_get_xh_intermed"); }
+int c2b_get_phih(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_phih, h->ncell * 8, "c2b_get_phih"); }
+int c2b_get_phih_f32(c2b_handle* h, float* p) {
+  C2B_CHECK_H(h);
+  if (!p) return fail(h, "c2b_get_phih_f32: null pointer");
+  if (bind_device(h)) return 1;
+  if (!h->d_f32tmp) CU(h, cudaMalloc(&h->d_f32tmp, h->ncell * sizeof(float)));
+  launch_to_f32(h->d_phih, h->d_f32tmp, h->ncell, h->stream);
+  h->launches += 1;
+  return download(h, p, h->d_f32tmp, h->ncell * 4, "c2b_get_phih_f32");
+}
+int c2b_get_source_nbox(c2b_handle* h, int32_t* nbox) {
+  C2B_CHECK_H(h);
+  if (!nbox) return fail(h, "c2b_get_source_nbox: null pointer");
+  if (h->NumSrc > 0) memcpy(nbox, h->h_nbox, (size_t)h->NumSrc * sizeof(int));
+  return 0;
+}
+int c2b_get_source_loss(c2b_handle* h, double* loss) {
+  C2B_CHECK_H(h);
+  if (!loss) return fail(h, "c2b_get_source_loss: null pointer");
+  if (h->NumSrc > 0) memcpy(loss, h->h_loss, (size_t)h->NumSrc * sizeof(double));
+  return 0;
+}
+
+int c2b_get_iter_state(c2b_handle* h, int32_t* niter, double* photon_loss_all, double* phih, double* xh_av,
+                       double* xh_intermed) {
+  C2B_CHECK_H(h);
+  if (niter) *niter = h->iter_niter;
+  if (photon_loss_all) *photon_loss_all = h->iter_photon_loss_all;
+  int rc = 0;
+  if (phih && (rc = c2b_get_phih(h, phih))) return rc;
+  if (xh_av && (rc = c2b_get_xh_av(h, xh_av))) return rc;
+  if (xh_intermed && (rc = c2b_get_xh_intermed(h, xh_intermed))) return rc;
+  return 0;
+}
+
+int c2b_set_iter_state(c2b_handle* h, int32_t niter, double photon_loss_all, const double* phih,
+                       const double* xh_av, const double* xh_intermed) {
+  C2B_CHECK_H(h);
+  if (!phih || !xh_av || !xh_intermed) return fail(h, "c2b_set_iter_state: null pointer");
+  if (bind_device(h)) return 1;
+  const size_t b = h->ncell * sizeof(double);
+  CU(h, cudaMemcpyAsync(h->d_phih, phih, b, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_xh_av, xh_av, b, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_xh_intermed, xh_intermed, b, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->iter_niter = niter;
+  h->iter_photon_loss_all = photon_loss_all;
+  h->have_iter_state = true;
+  return 0;
+}
+
+void* c2b_dev_ptr(c2b_handle* h, const char* name) {
+  if (!h || !name) return nullptr;
+  if (!strcmp(name, "ndens")) return h->d_ndens;
+  if (!strcmp(name, "xh")) return h->d_xh;
+  if (!strcmp(name, "xh_av")) return h->d_xh_av;
+  if (!strcmp(name, "xh_intermed")) return h->d_xh_intermed;
+  if (!strcmp(name, "phih")) return h->d_phih;
+  return nullptr;
+}
+
+int c2b_synchronize(c2b_handle* h) {
+  C2B_CHECK_H(h);
+  if (bind_device(h)) return 1;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int c2b_trace_source_debug(c2b_handle* h, int32_t ns, double* coldensh_out, double* phih, int32_t* nbox,
+                           double* photon_loss_src) {
+  C2B_CHECK_H(h);
+  if (int rc = check_ready(h)) return rc;
+  if (ns < 1 || ns > h->NumSrc) return fail(h, "c2b_trace_source_debug: source number out of range");
+  if (bind_device(h)) return 1;
+  double* d_dbg = nullptr;
+  int* d_one = nullptr;
+  CU(h, cudaMalloc(&d_dbg, h->ncell * sizeof(double)));
+  CU(h, cudaMalloc(&d_one, sizeof(int)));
+  const int idx = ns - 1;
+  CU(h, cudaMemcpyAsync(d_one, &idx, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(d_dbg, 0, h->ncell * sizeof(double), h->stream));
+  CU(h, cudaMemsetAsync(h->d_phih, 0, h->ncell * sizeof(double), h->stream));
+  // the trace reads xh_av; outside evolve3D that is the caller's responsibility (tests copy xh)
+  int rc = trace_sources(h, d_one, 1, d_dbg, nullptr);
+  if (!rc && coldensh_out) rc = download(h, coldensh_out, d_dbg, h->ncell * 8, "coldensh_out");
+  if (!rc && phih) rc = download(h, phih, h->d_phih, h->ncell * 8, "phih");
+  int nb = 0;
+  double ls = 0.0;
+  if (!rc) rc = download(h, &nb, h->d_nbox + idx, sizeof(int), "nbox");
+  if (!rc) rc = download(h, &ls, h->d_loss + idx, sizeof(double), "loss");
+  if (nbox) *nbox = nb;
+  if (photon_loss_src) *photon_loss_src = ls;
+  cudaFree(d_dbg);
+  cudaFree(d_one);
+  return rc;
+}
+
+int c2b_measure_dfma_rate(c2b_handle* h, double* dfma_per_s) {
+  C2B_CHECK_H(h);
+  if (!dfma_per_s) return fail(h, "c2b_measure_dfma_rate: null pointer");
+  if (bind_device(h)) return 1;
+  *dfma_per_s = measure_dfma_rate(h->stream);
+  h->launches += 4;
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

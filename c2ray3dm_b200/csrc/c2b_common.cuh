@@ -1,0 +1,95 @@
+// Shared declarations of the B200-native C2-Ray hot path (internal; the public ABI is
+// include/c2ray_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/c2ray_b200.h"
+
+namespace c2b {
+
+constexpr int kNumTau = C2B_NUMTAU;
+constexpr int kTableLen = kNumTau + 1;
+
+// ---- ray tracer ------------------------------------------------------------------------------
+// One work item = one source.  A source is traced shell by shell (Chebyshev distance r from the
+// source); the shell is stored as 24 "face quadrants" q = (principal axis p, sign of the principal
+// offset, signs of the two transverse offsets), each a square (r+1) x (r+1) patch of the plane
+// |d_p| = r indexed by the transverse distances (a, b).  A cell of plane r depends only on the
+// four cells (a-1|a, b-1|b) of plane r-1 of the same quadrant (column_density.f90:108-171).
+struct RtParams {
+  int n[3];                 // mesh
+  int lim[3][2];            // [axis][0: negative side L, 1: positive side R], evolve_source.F90:100-102
+  int subboxsize;
+  int plane_stride;         // S = max(lim)+1: quadrant patch is S x S doubles
+  const float* ndens;       // density_module.F90:22
+  const double* xh_av;      // evolve_data.F90:52
+  double* phih;             // evolve_data.F90:40
+  const float* lls_grid;    // LLS.F90:81 (type_of_LLS == 2) or nullptr
+  const double* thick;      // stellar_photo_thick_table(0:NumTau,1)
+  const double* thin;
+  const int* srcpos;        // 3 x NumSrc, 1-based (sourceprops.F90:56)
+  const double* normflux;   // NormFlux_stellar(1:NumSrc)
+  const int* work;          // source indices (0-based) this rank traces, in order
+  int nwork;
+  unsigned int* ticket;     // dynamic work counter (plays do_grid_master, master_slave.F90:124-231)
+  double* scratch;          // per-CTA plane storage: [grid][2][24][S][S]
+  int* nbox_out;            // per source (global index)
+  double* loss_out;         // per source
+  double* coldens_dbg;      // optional full coldensh_out grid (debug/parity), or nullptr
+  double S_star, dr[3], vol;
+  int use_lls, type_lls;
+  double coldensh_lls, rmax_lls2;
+  double sigma_HI, max_coldensh, tau_photo_limit, minlogtau, dlogtau, loss_fraction;
+  double epsilon, pi, sqrt2, sqrt3;
+};
+
+void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream);
+int raytrace_max_grid();   // resident CTAs of the ray-trace kernel on the current device
+size_t raytrace_scratch_doubles_per_cta(int plane_stride);
+
+// ---- per-cell chemistry + fused statistics ------------------------------------------------------
+constexpr int kNumStat = 8;
+// slots of the per-block partials
+enum StatSlot { kSumXh = 0, kH0 = 1, kH1 = 2, kRec = 3, kColl = 4, kMaxXhAv = 5, kConv = 6, kSpare = 7 };
+
+struct ChemParams {
+  size_t ncell;
+  const float* ndens;
+  const double* xh;        // ionfractions_module.F90:22 (start of step)
+  double* xh_av;           // in: previous iterate, out: new time average
+  double* xh_intermed;     // out
+  const double* phih;
+  const float* clumping_grid;  // type 3/4/5 or nullptr
+  float clumping;              // scalar (default real, clumping_module.F90:17)
+  double dt;
+  double bh00_powT;        // bh00*(T/1e4)**albpow is formed as (clumping*bh00)*powT, doric.f90:74
+  double bh00, powT;
+  double acolh0;           // colh0*sqrt(T)*exp(-temph0/T), doric.f90:77
+  double colh0, sqrtT, expT;  // the same three factors, multiplied per cell in total_rates order
+  double abu_c, epsilon, minimum_fractional_change, minimum_fraction_of_atoms;
+  double* partials;        // [nblocks][kNumStat]
+};
+
+void launch_chemistry(const ChemParams& p, int nblocks, cudaStream_t stream);
+// statistics only: sum(x_l), h0/h1 from (ndens,x_l); totrec/totcoll from (ndens,x_r) (x_r may be null)
+void launch_stats(const ChemParams& p, const double* x_l, const double* x_r, int nblocks,
+                  cudaStream_t stream);
+void launch_finalize_partials(const double* partials, int nblocks, double* out /*kNumStat*/,
+                              cudaStream_t stream);
+void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream);
+void launch_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
+int chemistry_blocks();
+
+// ---- rate tables (rad_ini) -----------------------------------------------------------------------
+struct SedParams {
+  double T_eff, S_star, freq_min, freq_max, hplanck, k_B, two_pi_over_c_square, R_solar, pi;
+  double pl_index_cross_section;
+  double minlogtau, dlogtau;
+};
+int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin, cudaStream_t stream,
+                           double* S_star_unscaled_out);
+
+double measure_dfma_rate(cudaStream_t stream);
+
+}  // namespace c2b

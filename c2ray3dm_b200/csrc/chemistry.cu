@@ -1,0 +1,240 @@
+// Per-cell pass of C2-Ray3Dm (sm_100a): global_pass's triple loop (evolve.F90:548-555) over
+// evolve0D_global + do_chemistry + doric (evolve_point.F90:305-555, doric.f90:33-134,
+// tped.f90:75-83), fused with every grid reduction the outer loop needs afterwards:
+// sum(xh_intermed) (evolve.F90:183,565), maxval(xh_av) of the previous iterate (:535), conv_flag
+// (:558), state_after and total_rates (photonstatistics.F90:137-217).
+//
+// One thread per cell, i fastest, so every grid is streamed exactly once with coalesced accesses.
+// Reductions are warp shuffle -> shared memory -> one partial row per CTA; a second single-CTA
+// kernel adds the rows in a fixed order, so the result is bit-reproducible run to run and
+// identical on every GPU that holds the same grids (the reference's replicas stay identical the
+// same way: every MPI rank runs the same serial loop).
+//
+// Compiled with -fmad=false to stay within rounding of the CPU restatement.
+#include "c2b_common.cuh"
+
+namespace c2b {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Acc {
+  double sum_x, h0, h1, rec, coll, maxav;
+  double conv;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ void block_store(const Acc& a, double* partials) {
+  __shared__ double s[kNumStat][kThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double v[kNumStat] = {warp_sum(a.sum_x), warp_sum(a.h0), warp_sum(a.h1), warp_sum(a.rec),
+                        warp_sum(a.coll), warp_max(a.maxav), warp_sum(a.conv), 0.0};
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kNumStat; ++k) s[k][wid] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumStat) {
+    const int k = threadIdx.x;
+    double t = s[k][0];
+    for (int w = 1; w < kThreads / 32; ++w) t = (k == kMaxXhAv) ? fmax(t, s[k][w]) : t + s[k][w];
+    partials[(size_t)blockIdx.x * kNumStat + k] = t;
+  }
+}
+
+// doric.f90:33-134 for the isothermal case; brech0 and acolh0 are cell-invariant up to clumping
+__device__ __forceinline__ void doric(double dt, double rhe, double brech0, double acolh0, double phih,
+                                      double eps, double xold1, double xold0, double& x1, double& x0,
+                                      double& xav1, double& xav0) {
+  const double aih0 = phih + rhe * acolh0;
+  const double delth = aih0 + rhe * brech0;
+  const double eqxfh1 = aih0 / delth;
+  const double eqxfh0 = rhe * brech0 / delth;
+  const double deltht = delth * dt;
+  const double ee = exp(-deltht);
+  x1 = (xold1 - eqxfh1) * ee + eqxfh1;
+  x0 = (xold0 - eqxfh0) * ee + eqxfh0;
+  if (x0 < eps) {
+    x0 = eps;
+    x1 = 1.0 - eps;
+  }
+  const double avg_factor = (deltht < (double)1.0e-8f) ? 1.0 : (1.0 - ee) / deltht;
+  xav1 = eqxfh1 + (xold1 - eqxfh1) * avg_factor;
+  xav0 = 1.0 - xav1;
+  if (xav0 < eps) xav0 = eps;
+}
+
+__global__ void __launch_bounds__(kThreads) chemistry_kernel(ChemParams P) {
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, -1.0e300, 0.0};
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x; c < P.ncell; c += stride) {
+    // evolve0D_global, evolve_point.F90:348-353 (no epsilon clamp on the neutral fractions)
+    const double xav_prev = P.xh_av[c];
+    const double h_old1 = fmax(P.epsilon, P.xh[c]);
+    const double h_old0 = 1.0 - h_old1;
+    double h_av1 = fmax(P.epsilon, xav_prev);
+    double h_av0 = 1.0 - h_av1;
+    const double ndens_p = (double)P.ndens[c];
+    const double phih = P.phih[c];
+    const float clump = P.clumping_grid ? P.clumping_grid[c] : P.clumping;  // clumping_point
+    const double brech0 = (double)clump * P.bh00 * P.powT;                  // doric.f90:74
+    double h1 = 0.0, h0 = 0.0;
+    // do_chemistry, evolve_point.F90:448-551
+    int nit = 0;
+    for (;;) {
+      nit += 1;
+      const double yh0_av_old = h_av0;
+      const double de = ndens_p * (h_av1 + P.abu_c);  // electrondens, tped.f90:75-83
+      doric(P.dt, de, brech0, P.acolh0, phih, P.epsilon, h_old1, h_old0, h1, h0, h_av1, h_av0);
+      if (fabs((h_av0 - yh0_av_old) / h_av0) < P.minimum_fractional_change ||
+          h_av0 < P.minimum_fraction_of_atoms)
+        break;
+      if (nit > 400) break;  // 'Convergence failing (global)'
+    }
+    // convergence against the previous iterate, evolve_point.F90:378-391
+    const double yh0_prev = 1.0 - fmax(P.epsilon, xav_prev);
+    const double dabs = fabs(h_av0 - yh0_prev);
+    if (dabs > P.minimum_fractional_change &&
+        fabs((h_av0 - yh0_prev) / h_av0) > P.minimum_fractional_change &&
+        h_av0 > P.minimum_fraction_of_atoms)
+      acc.conv += 1.0;
+    P.xh_intermed[c] = h1;  // :400-401
+    P.xh_av[c] = h_av1;
+    // fused reductions
+    acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
+    acc.sum_x += h1;                                       // :565
+    acc.h0 += ndens_p * (1.0 - h1);                        // state_after(xh_intermed)
+    acc.h1 += ndens_p * h1;
+    const double yh1 = h_av1, yh0 = 1.0 - h_av1;           // total_rates(dt,xh_av)
+    const double ne = ndens_p * (yh1 + P.abu_c);
+    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
+    acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+  }
+  block_store(acc, P.partials);
+}
+
+// state_before / state_after / total_rates without the chemistry (photonstatistics.F90:104-217)
+__global__ void __launch_bounds__(kThreads) stats_kernel(ChemParams P, const double* x_l,
+                                                         const double* x_r) {
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, -1.0e300, 0.0};
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x; c < P.ncell; c += stride) {
+    const double ndens_p = (double)P.ndens[c];
+    const double xl = x_l[c];
+    acc.sum_x += xl;
+    acc.h0 += ndens_p * (1.0 - xl);
+    acc.h1 += ndens_p * xl;
+    if (x_r) {
+      const double yh1 = x_r[c], yh0 = 1.0 - yh1;
+      const float clump = P.clumping_grid ? P.clumping_grid[c] : P.clumping;
+      const double ne = ndens_p * (yh1 + P.abu_c);
+      acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
+      acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+      acc.maxav = fmax(acc.maxav, yh1);
+    }
+  }
+  block_store(acc, P.partials);
+}
+
+__global__ void finalize_kernel(const double* partials, int nblocks, double* out) {
+  // one warp per statistic; fixed order => reproducible
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k >= kNumStat) return;
+  double t = (k == kMaxXhAv) ? -1.0e300 : 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    const double v = partials[(size_t)b * kNumStat + k];
+    t = (k == kMaxXhAv) ? fmax(t, v) : t + v;
+  }
+  t = (k == kMaxXhAv) ? warp_max(t) : warp_sum(t);
+  if (lane == 0) out[k] = t;
+}
+
+__global__ void scale_density_kernel(float* ndens, size_t n, double zfactor3) {
+  // ndens(:,:,:)=ndens(:,:,:)/zfactor3 (cosmology.F90:186): real(4)/real(8) -> real(8) -> real(4)
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride)
+    ndens[c] = (float)((double)ndens[c] / zfactor3);
+}
+
+__global__ void to_f32_kernel(const double* in, float* out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride)
+    out[c] = (float)in[c];
+}
+
+__global__ void dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+  double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+int chemistry_blocks() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * 8;  // 8 resident CTAs of 256 threads per SM
+}
+
+void launch_chemistry(const ChemParams& p, int nblocks, cudaStream_t stream) {
+  chemistry_kernel<<<nblocks, kThreads, 0, stream>>>(p);
+}
+void launch_stats(const ChemParams& p, const double* x_l, const double* x_r, int nblocks,
+                  cudaStream_t stream) {
+  stats_kernel<<<nblocks, kThreads, 0, stream>>>(p, x_l, x_r);
+}
+void launch_finalize_partials(const double* partials, int nblocks, double* out, cudaStream_t stream) {
+  finalize_kernel<<<1, 32 * kNumStat, 0, stream>>>(partials, nblocks, out);
+}
+void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream) {
+  scale_density_kernel<<<chemistry_blocks(), 256, 0, stream>>>(ndens, n, zfactor3);
+}
+void launch_to_f32(const double* in, float* out, size_t n, cudaStream_t stream) {
+  to_f32_kernel<<<chemistry_blocks(), 256, 0, stream>>>(in, out, n);
+}
+
+double measure_dfma_rate(cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 4, threads = 512, iters = 1 << 16;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dfma_kernel<<<blocks, threads, 0, stream>>>(d, 1 << 10);  // warm-up
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, stream);
+    dfma_kernel<<<blocks, threads, 0, stream>>>(d, iters);
+    cudaEventRecord(e1, stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
+    if (rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
+}  // namespace c2b
