@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native C2-Ray3Dm photo-ionization hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU restatement of the reference
+
+metric: cell-source ray-trace updates/s (one update = one evolve0D call passing the gate of
+evolve_point.F90:128), whole job.  A step is one evolve3D(dt) call (evolve.F90:83): all outer
+iterations of {ray-trace every source, reduce the rate grid over ranks, per-cell chemistry}.
+
+Workload (N=1): BASELINE.json configs[2] -- synthetic log-normal density 256^3, 10^4 sources at the
+density peaks, clumping grid on, LLS on, mid-reionization bubble state -- the largest configuration that
+fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling): every GPU
+holds the full grids and traces its round-robin share (master_slave.F90:85), the partial rate grids are
+summed with ncclAllReduce (evolve.F90:599-602).
+
+The reference is Fortran and cannot be built in this image (no Fortran compiler), so the reference arm
+and cpu_baseline time the C restatement in oracle/ ("kind": "port") on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cell-source raytrace updates/s"
+UNIT = "updates/s"
+B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 + xh_av 8 + phih RMW 16
+YEAR = 3.15576e7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mesh", type=int, default=256)
+    ap.add_argument("--nsrc", type=int, default=10000, help="sources per GPU")
+    ap.add_argument("--dt-myr", type=float, default=0.5)
+    ap.add_argument("--bubble", type=float, default=10.0, help="radius (cells) of the brightest source's bubble")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="sources in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def build_workload(mesh, nsrc_total, bubble):
+    """inputs of configs[2]/[3], deterministic"""
+    from c2ray3dm_b200 import synthetic as syn
+    zred = 9.0
+    seed = 20240607 if mesh == 256 else (20240608 if mesh == 512 else 20240600 + mesh)
+    nd = syn.lognormal_density(mesh, zred, seed)
+    pos, nf = syn.sources_at_density_peaks(nd, nsrc_total, 1e7)
+    radius = bubble * (nf / nf.max()) ** (1.0 / 3.0)
+    xh = syn.bubble_state(nd.shape, pos, radius)
+    dr, vol = syn.proper_geometry(mesh, zred)
+    return dict(zred=zred, ndens=nd, srcpos=pos, normflux=nf, xh=xh, dr=dr, vol=vol,
+                clumping=syn.clumping_from_density(nd, zred), coldensh_LLS=syn.lls_coldens(dr[0], zred))
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_sample(w, mesh, nsample, threads):
+    """times the C restatement (oracle/) on a bounded sample: one pass over every k-th source + one
+    per-cell pass, on `threads` host threads (sources dealt to threads, private rate grids summed: the
+    reference's MPI picture).  Returns (updates/s, description, seconds)."""
+    from oracle import oracle as O
+    ns = len(w["normflux"])
+    stride = max(1, ns // max(1, nsample))
+    sel = np.arange(0, ns, stride)[:nsample]
+    o = O.Oracle(mesh)
+    o.set_density(w["ndens"])
+    o.set_geometry(w["dr"], w["vol"])
+    o.set_clumping(5, 1.0, w["clumping"])
+    o.set_lls(True, 1, w["coldensh_LLS"], None, 0.0)
+    o.set_sources(w["srcpos"][sel], w["normflux"][sel], 1e48)
+    o.set_xh(w["xh"])
+    o.set_threads(threads)
+    o.xh_av[...] = w["xh"]
+    o.xh_intermed[...] = w["xh"]
+    o.state_before()
+    o.set_rates_to_zero()
+    t0 = time.perf_counter()
+    r = o.pass_all_sources()
+    t1 = time.perf_counter()
+    o.global_pass(0.5e6 * YEAR, r.photon_loss_all)
+    t2 = time.perf_counter()
+    desc = ("%d of %d sources (every %dth, file order) of the %d^3 workload: 1 pass_all_sources (%.2fs) + "
+            "1 global_pass (%.2fs), C restatement, %d threads source-parallel" % (
+                len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads))
+    return r.updates / (t1 - t0), desc, t2 - t0, r.updates
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    w = build_workload(args.mesh, args.nsrc * args.gpus, args.bubble)
+    nsample = args.cpu_sample or max(cores * 4, 64)
+    rates, secs, upd = [], [], []
+    desc = ""
+    for i in range(args.warmup + args.steps):
+        if i == 1 and args.warmup > 1:
+            pass
+        v, desc, s, u = cpu_sample(w, args.mesh, nsample, cores)
+        if i >= args.warmup:
+            rates.append(v)
+            secs.append(s)
+            upd.append(u)
+        if i == 0 and s > 60:   # keep the whole run within minutes
+            nsample = max(8, int(nsample * 30 / s))
+    value = float(np.sum(upd) / np.sum([u / r for u, r in zip(upd, rates)]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is Fortran and cannot be built in this image (no Fortran compiler): this is the C "
+                    "restatement in oracle/ on the host cores"}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "synthetic lognormal density %d^3, %d sources/GPU at density peaks, clumping grid (type 5), "
+                        "LLS type 1, bubble state r<=%g cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
+                            args.mesh, args.nsrc, args.bubble, args.dt_myr),
+            "mesh": args.mesh, "sources_total": args.nsrc * args.gpus, "parallelism": "source-sharded x%d" % args.gpus,
+            "l2": "grids (ndens+xh_av+phih = %.0f MB) exceed the 126 MB L2" % (20 * args.mesh ** 3 / 1e6)
+            if args.mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from c2ray3dm_b200 import Evolve
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA library is the product (no CPU fallback). "
+                         "Use --impl reference for the CPU restatement.")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mesh = args.mesh
+    w = build_workload(mesh, args.nsrc * world, args.bubble)
+    dt = args.dt_myr * 1e6 * YEAR
+
+    e = Evolve(mesh, device=local, rank=rank, nranks=world, type_of_clumping=5, use_LLS=True, type_of_LLS=1)
+    if world > 1:
+        uid = [Evolve.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        e.comm_init(uid[0])
+    e.rad_ini()
+    e.set_geometry(w["dr"], w["vol"])
+    e.set_clumping(w["clumping"])
+    e.set_LLS(coldensh_LLS=w["coldensh_LLS"])
+    e.set_sources(w["srcpos"], w["normflux"])
+    # pinned host staging for the end-to-end leg
+    nd_pin = torch.from_numpy(w["ndens"].reshape(-1)).pin_memory()
+    xh_pin = torch.from_numpy(w["xh"].reshape(-1).copy()).pin_memory()
+    e.set_density(nd_pin.numpy())
+    e.set_xh(xh_pin.numpy())
+
+    def barrier():
+        torch.cuda.synchronize()
+        e.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tsim = 0.0
+    reports = []
+    for _ in range(args.warmup):
+        reports.append(e.evolve3D(tsim, dt))
+        tsim += dt
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: state resident in HBM -------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    upd = launches = 0
+    ms_rt = ms_chem = ms_ar = ms_dev = 0.0
+    niter = 0
+    for _ in range(args.steps):
+        rep = e.evolve3D(tsim, dt)
+        tsim += dt
+        upd += rep.total_updates
+        launches += rep.kernel_launches
+        ms_rt += rep.ms_raytrace
+        ms_chem += rep.ms_chemistry
+        ms_ar += rep.ms_allreduce
+        ms_dev += rep.ms_total
+        niter += rep.niter
+    barrier()
+    wall = maxreduce(time.perf_counter() - t0)
+    ms_rt_max = maxreduce(ms_rt)
+    # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        xh_out = torch.empty(mesh ** 3, dtype=torch.float64).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        upd2 = 0
+        for _ in range(args.steps):
+            e.set_density(nd_pin.numpy())     # what the host re-sends after cosmo_evol (cosmology.F90:186)
+            e.set_xh(xh_pin.numpy())          # ionfractions_module.F90:22
+            rep = e.evolve3D(tsim, dt)
+            xh_np = xh_out.numpy()
+            e._ck(e.L.c2b_get_xh(e.h, xh_np.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))), "c2b_get_xh")
+            xh_pin.copy_(xh_out)              # next step starts from the returned state, as the host would
+            tsim += dt
+            upd2 += rep.total_updates
+        barrier()
+        wall2 = maxreduce(time.perf_counter() - t0)
+        e2e = {"value": upd2 / wall2, "unit": UNIT, "h2d_bytes_per_step": 12 * mesh ** 3,
+               "d2h_bytes_per_step": 8 * mesh ** 3, "ms_per_step": 1e3 * wall2 / args.steps}
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+    peak, peak_kind = load_peaks()
+    dfma = e.measure_dfma_rate()
+    line = None
+    if rank == 0:
+        # updates of THIS rank's ray-trace kernels over their device time (CUDA events on the launch stream)
+        upd_rank = upd / world
+        achieved = upd_rank * B_RT / (ms_rt_max * 1e-3) / 1e9 if ms_rt_max > 0 else 0.0
+        line = {"metric": METRIC, "value": upd / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args),
+                "seconds_per_evolve3D_step": wall / args.steps,
+                "updates_per_step": upd / args.steps, "outer_iterations_per_step": niter / args.steps,
+                "gpu_launches": int(launches),
+                "phase_ms_per_step": {"raytrace": ms_rt / args.steps, "allreduce": ms_ar / args.steps,
+                                      "chemistry": ms_chem / args.steps, "device_total": ms_dev / args.steps},
+                "roofline": {"kernel": "raytrace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind,
+                             "algorithmic_bytes_per_update": B_RT,
+                             "note": "FP64-issue bound expected to bind first (SURVEY 8d)"},
+                "fp64": {"dfma_per_s_measured": dfma,
+                         "updates_per_s_per_gpu_raytrace": upd_rank / (ms_rt_max * 1e-3) if ms_rt_max > 0 else 0.0},
+                "clocks": sampler.summary(),
+                "e2e": e2e}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nsample = args.cpu_sample or max(cores * 4, 64)
+        v, desc, s, u = cpu_sample(w, mesh, nsample, cores)
+        if s < 5:  # scale the sample towards ~10-30 s of CPU work
+            nsample = min(len(w["normflux"]), int(nsample * 15 / max(s, 1e-3)))
+            v, desc, s, u = cpu_sample(w, mesh, nsample, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    e.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

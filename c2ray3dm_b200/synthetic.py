@@ -51,7 +51,7 @@ def lognormal_density(N, zred, seed, sigma=1.0, smooth_cells=2.0):
     ky = k[None, :, None]
     kx = np.fft.rfftfreq(N).astype(np.float32)[None, None, :] * 2.0 * np.pi
     filt = np.exp(-0.5 * smooth_cells ** 2 * (kx * kx + ky * ky + kz * kz))
-    g = np.fft.irfftn(np.fft.rfftn(g) * filt, s=(N, N, N)).astype(np.float64)
+    g = np.fft.irfftn(np.fft.rfftn(g) * filt, s=(N, N, N), axes=(0, 1, 2)).astype(np.float64)
     g = (g - g.mean()) / g.std()
     return (avg_dens(zred) * np.exp(sigma * g - 0.5 * sigma * sigma)).astype(np.float32)
 

@@ -1,0 +1,379 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+the CPU oracle on the same seeded inputs, against the committed golden fixtures, and -- at sizes the
+oracle cannot reach -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): ionized fractions abs 1e-6, photo-ionization rates rel 1e-6,
+photon statistics rel 1e-6; shell/cell indexing, nbox and update counts exact."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from problems import make_problem, setup_oracle, setup_gpu
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RATE_RTOL = 1e-6
+X_ATOL = 1e-6
+DT = 1e6 * 3.15576e7
+
+
+def _rates_close(gpu, cpu, rtol=RATE_RTOL):
+    """relative tolerance on every cell that has a rate; cells the oracle leaves at exactly 0 must be 0"""
+    gpu = np.asarray(gpu).reshape(-1)
+    cpu = np.asarray(cpu).reshape(-1)
+    nz = cpu != 0
+    assert np.array_equal(gpu == 0, cpu == 0), "sets of cells with a rate differ"
+    err = np.max(np.abs(gpu[nz] - cpu[nz]) / np.abs(cpu[nz])) if nz.any() else 0.0
+    assert err <= rtol, "max relative rate error %.3e" % err
+    return err
+
+
+CASES = [
+    dict(N=16, nsrc=1, seed=1, state="ionized", use_LLS=False),
+    dict(N=21, nsrc=3, seed=5, state="ionized", use_LLS=False),               # odd mesh
+    dict(N=24, nsrc=3, seed=5, state="ionized", use_LLS=True),
+    dict(N=(16, 20, 12), nsrc=3, seed=5, state="ionized", use_LLS=False),      # non-cubic
+    dict(N=22, nsrc=2, seed=6, state="ionized", use_LLS=False),               # the -N/2 layer quirk
+    dict(N=32, nsrc=8, seed=7, state="random", use_LLS=True),
+    dict(N=32, nsrc=8, seed=7, state="random", use_LLS=True, type_of_LLS=2, clumping="grid"),
+    dict(N=32, nsrc=8, seed=7, state="ionized", use_LLS=True, type_of_LLS=3),
+    dict(N=32, nsrc=5, seed=8, state="neutral", use_LLS=True),                 # every ray stops in subbox 1
+    dict(N=48, nsrc=64, seed=9, state="random", use_LLS=True, clumping="scalar2"),
+]
+
+
+def _problem(c):
+    p = make_problem(**c)
+    if c["state"] == "random":
+        p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    return p
+
+
+@pytest.fixture(scope="module")
+def gpu_tables():
+    p = make_problem(8)
+    e = setup_gpu(p)
+    t = e.rad_ini()
+    e.close()
+    return t
+
+
+def test_tables_match_oracle(gpu_tables):
+    """rad_ini on the device vs the restated rad_ini (exp/pow differ by an ulp at most)"""
+    from oracle import oracle as O
+    thick, thin, _ = O.rad_ini()
+    np.testing.assert_allclose(gpu_tables[0], thick, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(gpu_tables[1], thin, rtol=1e-12, atol=0)
+    g = np.load(os.path.join(GOLD, "tables.npz"))
+    np.testing.assert_allclose(gpu_tables[0][g["idx"]], g["thick"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%s_%s_s%d" % (c["N"], c["state"], c["nsrc"]))
+def test_raytrace_pass_matches_oracle(case, gpu_tables):
+    p = _problem(case)
+    e = setup_gpu(p, tables=gpu_tables)
+    o = setup_oracle(p, tables=gpu_tables)
+    o.xh_av[...] = p["xh"]
+    o.set_rates_to_zero()
+    r = o.pass_all_sources()
+    e.begin_step()
+    g = e.pass_all_sources()
+    assert g.sum_nbox_all == r.sum_nbox_all           # shell / subbox indexing: exact
+    assert g.updates == r.updates                     # gate count: exact
+    assert g.photon_loss_all == pytest.approx(r.photon_loss_all, rel=RATE_RTOL)
+    _rates_close(e.phih_grid, o.phih)
+    # per source: subbox count exact, boundary loss within tolerance
+    nbox = e.source_nbox()
+    loss = e.source_loss()
+    for ns in range(1, len(p["normflux"]) + 1):
+        o1 = setup_oracle(p, tables=gpu_tables)
+        o1.xh_av[...] = p["xh"]
+        o1.set_rates_to_zero()
+        rr = o1.do_source(ns)
+        assert nbox[ns - 1] == rr.nbox
+        assert loss[ns - 1] == pytest.approx(rr.photon_loss_src, rel=RATE_RTOL, abs=0)
+        if ns > 3:
+            break
+    e.close()
+
+
+@pytest.mark.parametrize("case", CASES[:7], ids=lambda c: "N%s_%s" % (c["N"], c["state"]))
+def test_single_source_column_densities(case, gpu_tables):
+    """do_source for one source: the whole coldensh_out grid (rel 1e-12), the set of traced cells
+    (exact), the rates, nbox and the boundary loss"""
+    p = _problem(case)
+    e = setup_gpu(p, tables=gpu_tables)
+    e.begin_step()
+    o = setup_oracle(p, tables=gpu_tables)
+    o.xh_av[...] = p["xh"]
+    o.set_rates_to_zero()
+    rr = o.do_source(1)
+    cd, ph, nbox, loss = e.trace_source_debug(1)
+    assert nbox == rr.nbox
+    assert np.array_equal(cd == 0, o.coldensh_out == 0)
+    np.testing.assert_allclose(cd, o.coldensh_out, rtol=1e-12, atol=0)
+    _rates_close(ph, o.phih)
+    assert loss == pytest.approx(rr.photon_loss_src, rel=RATE_RTOL)
+    e.close()
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[5], CASES[6], CASES[9]],
+                         ids=lambda c: "N%s_%s" % (c["N"], c["state"]))
+def test_global_pass_matches_oracle(case, gpu_tables):
+    """the per-cell kernel alone: both start from the oracle's rate grid"""
+    p = _problem(case)
+    o = setup_oracle(p, tables=gpu_tables)
+    o.state_before()
+    o.xh_av[...] = p["xh"]
+    o.xh_intermed[...] = p["xh"]
+    o.set_rates_to_zero()
+    r = o.pass_all_sources()
+    e = setup_gpu(p, tables=gpu_tables)
+    e.begin_step()
+    e.set_iter_state(1, r.photon_loss_all, o.phih, o.xh_av, o.xh_intermed)
+    gg = e.global_pass(DT)
+    go = o.global_pass(DT, r.photon_loss_all)
+    assert gg.conv_flag == go.conv_flag
+    assert gg.min_avg_neutral == pytest.approx(go.min_avg_neutral, rel=1e-12)
+    np.testing.assert_allclose(e.xh_intermed, o.xh_intermed, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(e.xh_av, o.xh_av, rtol=0, atol=1e-12)
+    assert gg.sum_xh_intermed == pytest.approx(go.sum_xh_intermed, rel=1e-12)
+    for n in ("h0_after", "h1_after", "totrec", "totcollisions", "total_photon_loss", "totalsrc"):
+        assert getattr(gg.stats, n) == pytest.approx(getattr(go.stats, n), rel=1e-11), n
+    e.close()
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N%s_%s_s%d" % (c["N"], c["state"], c["nsrc"]))
+def test_evolve3d_step_matches_oracle(case, gpu_tables):
+    """one full evolve3D call: iteration count, per-iteration convergence counters, final fractions,
+    rates and the photon-conservation statistics"""
+    p = _problem(case)
+    o = setup_oracle(p, tables=gpu_tables)
+    ro = o.evolve3D(DT)
+    e = setup_gpu(p, tables=gpu_tables)
+    rg = e.evolve3D(0.0, DT)
+    assert (rg.niter, rg.converged, rg.conv_criterion) == (ro.niter, ro.converged, ro.conv_criterion)
+    assert list(rg.conv_flag[1:rg.niter + 1]) == list(ro.conv_flag[1:ro.niter + 1])
+    assert list(rg.sum_nbox_all[1:rg.niter + 1]) == list(ro.sum_nbox_all[1:ro.niter + 1])
+    assert rg.total_updates == ro.total_updates
+    assert rg.kernel_launches >= 3 * rg.niter
+    np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+    np.testing.assert_allclose(e.xh_av, o.xh_av, rtol=0, atol=X_ATOL)
+    np.testing.assert_allclose(e.xh_intermed, o.xh_intermed, rtol=0, atol=X_ATOL)
+    _rates_close(e.phih_grid, o.phih)
+    for n in ("totrec", "totcollisions", "dh0", "total_ion", "photcons", "total_photon_loss", "totalsrc",
+              "h0_before", "h1_after"):
+        a, b = getattr(rg.final_stats, n), getattr(ro.final_stats, n)
+        assert a == pytest.approx(b, rel=1e-6, abs=1e-6 * abs(ro.final_stats.totrec) if n in ("dh0", "total_ion") else 0), n
+    assert rg.grtotal_src == pytest.approx(ro.grtotal_src, rel=1e-12)
+    e.close()
+
+
+def test_history_three_steps_with_cosmology(gpu_tables):
+    """three consecutive steps with the host's cosmo_evol between them (C2Ray.F90:367-379)"""
+    p = _problem(dict(N=24, nsrc=6, seed=14, state="neutral", use_LLS=True, flux=3e8))
+    o = setup_oracle(p, tables=gpu_tables)
+    e = setup_gpu(p, tables=gpu_tables)
+    ndens = p["ndens"].copy()
+    dr, vol = p["dr"].copy(), p["vol"]
+    for step in range(3):
+        zf = 1.0 + 0.01 * (step + 1)
+        zf3 = zf * zf * zf
+        dr = dr * zf
+        vol = vol * zf3
+        ndens = (ndens.astype(np.float64) / zf3).astype(np.float32)
+        o.set_density(ndens)
+        o.set_geometry(dr, vol)
+        e.cosmo_evol(zf)
+        ro = o.evolve3D(DT)
+        rg = e.evolve3D(step * DT, DT)
+        assert rg.niter == ro.niter
+        np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+        assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
+        assert rg.grtotal_ion == pytest.approx(ro.grtotal_ion, rel=1e-6)
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["g16_lls", "g20_clump", "g12x16x10"])
+def test_against_committed_golden(name):
+    """the CUDA path against the committed fixtures (generated by tests/golden/make_golden.py)"""
+    sys.path.insert(0, GOLD)
+    import make_golden as mg
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    p = mg.make_case(name)
+    e = setup_gpu(p)
+    e.begin_step()
+    r = e.pass_all_sources()
+    assert r.sum_nbox_all == g["sum_nbox"] and r.updates == g["updates"]
+    _rates_close(e.phih_grid, g["phih_pass"])
+    assert r.photon_loss_all == pytest.approx(float(g["photon_loss_all"]), rel=RATE_RTOL)
+    e.set_xh(p["xh"])
+    rep = e.evolve3D(0.0, mg.DT)
+    assert rep.niter == g["niter"]
+    assert list(rep.conv_flag[:rep.niter + 1])[1:] == list(g["conv_flag"])[1:]
+    np.testing.assert_allclose(e.xh, g["xh"], rtol=0, atol=X_ATOL)
+    _rates_close(e.phih_grid, g["phih"])
+    assert rep.final_stats.photcons == pytest.approx(float(g["photcons"]), rel=1e-6)
+    e.close()
+
+
+def test_restart_from_iteration_state(gpu_tables):
+    """get/set_iter_state (iterdump, evolve.F90:285-426): stopping after 2 outer iterations and restarting
+    reaches the same converged answer as an uninterrupted call"""
+    p = _problem(CASES[5])
+    e = setup_gpu(p, tables=gpu_tables)
+    full = e.evolve3D(0.0, DT)
+    x_full = e.xh
+    e2 = setup_gpu(p, tables=gpu_tables, max_outer_iter=1)
+    part = e2.evolve3D(0.0, DT)
+    assert part.converged == 0 and part.niter == 2
+    niter, pl, phih, xav, xint = e2.get_iter_state()
+    e3 = setup_gpu(p, tables=gpu_tables)
+    e3.set_iter_state(niter, pl, phih, xav, xint)
+    rest = e3.evolve3D(0.0, DT, restart=1)
+    # the restart repeats one global_pass on the dumped state (evolve.F90:157), so it may need one more
+    # outer iteration and lands on the same fixed point within the outer convergence criterion
+    assert rest.converged == 1 and rest.niter in (full.niter, full.niter + 1)
+    np.testing.assert_allclose(e3.xh, x_full, rtol=0, atol=2e-4)
+    for x in (e, e2, e3):
+        x.close()
+
+
+def test_abi_error_paths_on_device():
+    from c2ray3dm_b200 import lib as L, C2RayError
+    p = make_problem(12, nsrc=2, seed=2)
+    e = setup_gpu(p)
+    lib = e.L
+    assert lib.c2b_set_density(e.h, None) != 0 and b"null" in lib.c2b_last_error(e.h)
+    assert lib.c2b_set_tables(e.h, None, None, 2001) != 0
+    t = np.zeros(10)
+    assert lib.c2b_set_tables(e.h, t.ctypes.data_as(C.POINTER(C.c_double)), t.ctypes.data_as(C.POINTER(C.c_double)), 10) != 0
+    bad = np.array([[0, 1, 1]], dtype=np.int32)
+    with pytest.raises(C2RayError):
+        e.set_sources(bad, [1.0])
+    with pytest.raises(C2RayError):
+        e.set_sources(np.array([[13, 1, 1]], dtype=np.int32), [1.0])
+    rep = L.StepReport()
+    assert lib.c2b_evolve3d(e.h, 0.0, -1.0, 0, C.byref(rep)) != 0
+    assert lib.c2b_evolve3d(e.h, 0.0, 1.0, 1, C.byref(rep)) != 0      # restart without state
+    # handle still usable afterwards
+    e.set_sources(p["srcpos"], p["normflux"])
+    assert e.evolve3D(0.0, DT).niter >= 1
+    # missing inputs are reported, not crashed on
+    e2 = __import__("c2ray3dm_b200").Evolve(12)
+    with pytest.raises(C2RayError) as ei:
+        e2.evolve3D(0.0, DT)
+    assert "not set" in str(ei.value)
+    e.close()
+    e2.close()
+
+
+def test_zero_and_empty_sources(gpu_tables):
+    p = _problem(dict(N=16, nsrc=3, seed=4, state="ionized"))
+    p["normflux"][1] = 0.0                      # never traced: adds 0 to sum_nbox
+    e = setup_gpu(p, tables=gpu_tables)
+    o = setup_oracle(p, tables=gpu_tables)
+    o.xh_av[...] = p["xh"]
+    o.set_rates_to_zero()
+    r = o.pass_all_sources()
+    e.begin_step()
+    g = e.pass_all_sources()
+    assert g.sum_nbox_all == r.sum_nbox_all and e.source_nbox()[1] == 0
+    _rates_close(e.phih_grid, o.phih)
+    e.set_sources(np.zeros((0, 3), dtype=np.int32), np.zeros(0))
+    g = e.pass_all_sources()
+    assert g.updates == 0 and not e.phih_grid.any()
+    e.close()
+
+
+def test_phih_single_precision_output(gpu_tables):
+    p = _problem(CASES[2])
+    e = setup_gpu(p, tables=gpu_tables)
+    e.begin_step()
+    e.pass_all_sources()
+    np.testing.assert_array_equal(e.phih_grid_si, e.phih_grid.astype(np.float32))   # real(phih_grid,si)
+    e.close()
+
+
+# ---- properties at sizes the oracle cannot reach ---------------------------------------------------
+def test_linearity_in_sources_at_128(gpu_tables):
+    """rates are additive over sources at fixed xh_av (evolve_point.F90:283): trace A, B and A+B on 128^3"""
+    from c2ray3dm_b200 import synthetic as syn
+    N = 128
+    nd = syn.lognormal_density(N, 9.0, 77)
+    pos, nf = syn.sources_at_density_peaks(nd, 40, 3e8)
+    xh = syn.bubble_state(nd.shape, pos, 9.0)
+    dr, vol = syn.proper_geometry(N, 9.0)
+    out = []
+    for sel in (slice(0, 20), slice(20, 40), slice(0, 40)):
+        e = __import__("c2ray3dm_b200").Evolve(N, use_LLS=True)
+        e.set_tables(*gpu_tables)
+        e.set_density(nd)
+        e.set_geometry(dr, vol)
+        e.set_LLS(coldensh_LLS=syn.lls_coldens(dr[0], 9.0))
+        e.set_sources(pos[sel], nf[sel])
+        e.set_xh(xh)
+        e.begin_step()
+        r = e.pass_all_sources()
+        out.append((e.phih_grid, r))
+        e.close()
+    np.testing.assert_allclose(out[0][0] + out[1][0], out[2][0], rtol=1e-10, atol=1e-30)
+    assert out[0][1].updates + out[1][1].updates == out[2][1].updates
+    assert out[0][1].photon_loss_all + out[1][1].photon_loss_all == pytest.approx(out[2][1].photon_loss_all, rel=1e-10)
+
+
+def test_translation_invariance_periodic(gpu_tables):
+    """periodic mesh: shifting density, state and sources by the same lattice vector shifts the rates"""
+    from c2ray3dm_b200 import synthetic as syn
+    N = 64
+    nd = syn.lognormal_density(N, 9.0, 5)
+    pos, nf = syn.sources_at_density_peaks(nd, 12, 1e8)
+    xh = syn.bubble_state(nd.shape, pos, 7.0)
+    dr, vol = syn.proper_geometry(N, 9.0)
+    shift = (17, 40, 3)  # (i,j,k)
+
+    def run(nd_, xh_, pos_):
+        e = __import__("c2ray3dm_b200").Evolve(N, use_LLS=False)
+        e.set_tables(*gpu_tables)
+        e.set_density(nd_)
+        e.set_geometry(dr, vol)
+        e.set_sources(pos_, nf)
+        e.set_xh(xh_)
+        rep = e.evolve3D(0.0, DT)
+        res = (e.phih_grid, e.xh, rep.niter)
+        e.close()
+        return res
+
+    a = run(nd, xh, pos)
+    roll = lambda g: np.roll(g, (shift[2], shift[1], shift[0]), axis=(0, 1, 2))
+    pos2 = ((pos - 1 + np.array(shift)) % N + 1).astype(np.int32)
+    b = run(roll(nd), roll(xh), pos2)
+    assert a[2] == b[2]
+    np.testing.assert_allclose(roll(a[0]), b[0], rtol=1e-9, atol=1e-30)   # xc=alam*di+real(i0) rounds with i0
+    np.testing.assert_allclose(roll(a[1]), b[1], rtol=0, atol=1e-9)
+
+
+@pytest.mark.skipif(os.environ.get("C2B_SLOW", "0") != "1", reason="one full-box source on 512^3: set C2B_SLOW=1")
+def test_full_box_update_count_512_quirk():
+    """N=512: R=255=5*51 stops the walk one pass before the -256 layer is reached: 511^3 updates per
+    fully-traced source.  Uses a tiny flux threshold so the trace covers the box."""
+    N = 512
+    import c2ray3dm_b200 as pkg
+    from c2ray3dm_b200 import synthetic as syn
+    e = pkg.Evolve(N, use_LLS=False, loss_fraction=0.0)
+    e.rad_ini()
+    e.set_density(np.full(N ** 3, syn.avg_dens(9.0), dtype=np.float32))
+    dr, vol = syn.proper_geometry(N, 9.0)
+    e.set_geometry(dr, vol)
+    e.set_sources(np.array([[100, 200, 300]], dtype=np.int32), [1e9])
+    e.set_xh(np.full(N ** 3, 1.0 - 1e-6))
+    e.begin_step()
+    r = e.pass_all_sources()
+    assert r.sum_nbox_all == 51
+    assert r.updates == 511 ** 3
+    ph = e.phih_grid
+    assert np.count_nonzero(ph) == 511 ** 3
+    e.close()
