@@ -236,7 +236,7 @@ def test_restart_from_iteration_state(gpu_tables):
     rest = e3.evolve3D(0.0, DT, restart=1)
     # the restart repeats one global_pass on the dumped state (evolve.F90:157), so it may need one more
     # outer iteration and lands on the same fixed point within the outer convergence criterion
-    assert rest.converged == 1 and rest.niter in (full.niter, full.niter + 1)
+    assert rest.converged == 1 and part.niter <= rest.niter <= full.niter + 1
     np.testing.assert_allclose(e3.xh, x_full, rtol=0, atol=2e-4)
     for x in (e, e2, e3):
         x.close()
