@@ -9,8 +9,8 @@ evolve_point.F90:128), whole job.  A step is one evolve3D(dt) call (evolve.F90:8
 iterations of {ray-trace every source, reduce the rate grid over ranks, per-cell chemistry}.
 
 Workload (N=1): BASELINE.json configs[2] -- synthetic log-normal density 256^3, 10^4 sources at the
-density peaks, clumping grid on, LLS on, mid-reionization bubble state -- the largest configuration that
-fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling): every GPU
+density peaks, clumping grid on, LLS on, mid-reionization bubble state (mean ionized fraction 0.54: spheres of up to
+25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling): every GPU
 holds the full grids and traces its round-robin share (master_slave.F90:85), the partial rate grids are
 summed with ncclAllReduce (evolve.F90:599-602).
 
@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--mesh", type=int, default=256)
     ap.add_argument("--nsrc", type=int, default=10000, help="sources per GPU")
     ap.add_argument("--dt-myr", type=float, default=0.5)
-    ap.add_argument("--bubble", type=float, default=10.0, help="radius (cells) of the brightest source's bubble")
+    ap.add_argument("--bubble", type=float, default=25.0, help="radius (cells) of the brightest source's bubble")
     ap.add_argument("--cpu-sample", type=int, default=0, help="sources in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -176,7 +176,7 @@ def run_reference(args):
 
 def workload_config(args):
     return {"workload": "synthetic lognormal density %d^3, %d sources/GPU at density peaks, clumping grid (type 5), "
-                        "LLS type 1, bubble state r<=%g cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
+                        "LLS type 1, mid-reionization bubble state r<=%g cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
                             args.mesh, args.nsrc, args.bubble, args.dt_myr),
             "mesh": args.mesh, "sources_total": args.nsrc * args.gpus, "parallelism": "source-sharded x%d" % args.gpus,
             "l2": "grids (ndens+xh_av+phih = %.0f MB) exceed the 126 MB L2" % (20 * args.mesh ** 3 / 1e6)

@@ -63,7 +63,10 @@ struct c2b_handle {
   float* d_ndens = nullptr;
   double *d_xh = nullptr, *d_xh_av = nullptr, *d_xh_intermed = nullptr, *d_phih = nullptr;
   float *d_clump = nullptr, *d_lls = nullptr, *d_f32tmp = nullptr;
-  double *d_thick = nullptr, *d_thin = nullptr;
+  double *d_thick = nullptr, *d_thin = nullptr, *d_taucell = nullptr;
+  double2 *d_thick2 = nullptr, *d_logtab = nullptr;
+  bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
+  int smem_plane_doubles = 0;
   bool have_tables = false, have_density = false, have_xh = false, have_geometry = false;
   // sources
   int NumSrc = 0, nwork = 0;
@@ -253,6 +256,20 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMalloc(&h->d_thick, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_ticket, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_taucell, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell", e);
+  if ((e = cudaMalloc(&h->d_thick2, kTableLen * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_logtab, 128 * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
+  {
+    // log2 table of the table-coordinate evaluation (raytrace.cu: table_coord)
+    const double B = std::log10(2.0) / cfg->dlogtau, A = 1.0 - cfg->minlogtau / cfg->dlogtau;
+    double2 lt[128];
+    for (int j = 0; j < 128; ++j) {
+      const double cj = 1.0 + (j + 0.5) / 128.0;
+      lt[j].x = 1.0 / cj;
+      lt[j].y = A + B * std::log2(cj);
+    }
+    if ((e = cudaMemcpy(h->d_logtab, lt, sizeof(lt), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("memcpy", e);
+  }
   // evolve_source.F90:100-102 (periodic_bc)
   int smax = 0;
   for (int d = 0; d < 3; ++d) {
@@ -261,7 +278,10 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
     smax = std::max(smax, std::max(h->lim[d][0], h->lim[d][1]));
   }
   h->plane_stride = smax + 1;
-  h->rt_grid = raytrace_max_grid();
+  int per_sm = 1, sms = 0;
+  if (raytrace_configure(smax, &h->smem_plane_doubles, &per_sm)) return bail("raytrace_configure", cudaGetLastError());
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  h->rt_grid = sms * per_sm;
   const size_t scratch = raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt_grid;
   if ((e = cudaMalloc(&h->d_scratch, scratch * sizeof(double))) != cudaSuccess) return bail("cudaMalloc scratch", e);
   h->chem_blocks = chemistry_blocks();
@@ -283,7 +303,7 @@ void c2b_destroy(c2b_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
-  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
+  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
   cudaFree(h->d_work); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
@@ -335,6 +355,8 @@ int c2b_set_tables(c2b_handle* h, const double* thick, const double* thin, int32
   if (bind_device(h)) return 1;
   CU(h, cudaMemcpyAsync(h->d_thick, thick, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_thin, thin, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_pair_table(h->d_thick, h->d_thick2, h->stream);
+  h->launches += 1;
   CU(h, cudaStreamSynchronize(h->stream));
   h->have_tables = true;
   return 0;
@@ -353,6 +375,9 @@ int c2b_rad_ini_blackbody(c2b_handle* h, double T_eff, double S_star, double fre
   int rc = build_blackbody_tables(sp, h->d_thick, h->d_thin, h->stream, nullptr);
   h->launches += 1;
   if (rc) return fail(h, "c2b_rad_ini_blackbody: table kernel failed");
+  launch_pair_table(h->d_thick, h->d_thick2, h->stream);
+  h->launches += 1;
+  CU(h, cudaStreamSynchronize(h->stream));
   h->have_tables = true;
   if (thick_out) CU(h, cudaMemcpy(thick_out, h->d_thick, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
   if (thin_out) CU(h, cudaMemcpy(thin_out, h->d_thin, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
@@ -366,6 +391,7 @@ int c2b_set_density(c2b_handle* h, const float* ndens) {
   CU(h, cudaMemcpyAsync(h->d_ndens, ndens, h->ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   h->have_density = true;
+  h->taucell_dirty = true;
   return 0;
 }
 
@@ -376,6 +402,7 @@ int c2b_set_geometry(c2b_handle* h, const double dr[3], double vol) {
   h->dr[0] = dr[0]; h->dr[1] = dr[1]; h->dr[2] = dr[2];
   h->vol = vol;
   h->have_geometry = true;
+  h->taucell_dirty = true;
   return 0;
 }
 
@@ -389,6 +416,7 @@ int c2b_cosmo_evol(c2b_handle* h, double zfactor) {
   h->vol = h->vol * zfactor3;
   launch_scale_density(h->d_ndens, h->ncell, zfactor3, h->stream);
   h->launches += 1;
+  h->taucell_dirty = true;
   CU(h, cudaGetLastError());
   return 0;
 }
@@ -516,6 +544,8 @@ static void fill_chem(c2b_handle* h, double dt, ChemParams& cp) {
   cp.minimum_fractional_change = c.minimum_fractional_change;
   cp.minimum_fraction_of_atoms = c.minimum_fraction_of_atoms;
   cp.partials = h->d_partials;
+  cp.tau_cell = h->d_taucell;
+  cp.sigma_dr0 = c.sigma_HI * h->dr[0];
 }
 
 static int fetch_stats(c2b_handle* h) {
@@ -573,12 +603,13 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* co
   }
   rp.subboxsize = c.subboxsize;
   rp.plane_stride = h->plane_stride;
-  rp.ndens = h->d_ndens;
-  rp.xh_av = h->d_xh_av;
+  rp.smem_plane_doubles = h->smem_plane_doubles;
+  rp.tau_cell = h->d_taucell;
   rp.phih = h->d_phih;
   rp.lls_grid = h->d_lls;
-  rp.thick = h->d_thick;
+  rp.thick2 = h->d_thick2;
   rp.thin = h->d_thin;
+  rp.logtab = h->d_logtab;
   rp.srcpos = h->d_srcpos;
   rp.normflux = h->d_normflux;
   rp.work = d_work;
@@ -592,18 +623,28 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* co
   rp.vol = h->vol;
   rp.use_lls = c.use_LLS;
   rp.type_lls = c.type_of_LLS;
-  rp.coldensh_lls = h->coldensh_LLS;
+  rp.tau_lls = c.sigma_HI * h->coldensh_LLS;
   rp.rmax_lls2 = h->R_max_LLS * h->R_max_LLS;
   rp.sigma_HI = c.sigma_HI;
+  rp.inv_sigma = 1.0 / c.sigma_HI;
+  rp.inv_sigma_dr0 = 1.0 / (c.sigma_HI * h->dr[0]);
+  rp.fourpi_over_sigma = 4.0 * c.pi / c.sigma_HI;
   rp.max_coldensh = c.max_coldensh;
   rp.tau_photo_limit = c.tau_photo_limit;
-  rp.minlogtau = c.minlogtau;
-  rp.dlogtau = c.dlogtau;
   rp.loss_fraction = c.loss_fraction;
-  rp.epsilon = c.epsilon;
-  rp.pi = c.pi;
   rp.sqrt2 = c.sqrt2;
   rp.sqrt3 = c.sqrt3;
+  rp.logB = std::log10(2.0) / c.dlogtau;
+  {
+    const double k = rp.logB / std::log(2.0);
+    rp.logc[0] = k; rp.logc[1] = -k / 2.0; rp.logc[2] = k / 3.0; rp.logc[3] = -k / 4.0; rp.logc[4] = k / 5.0;
+  }
+  if (h->taucell_dirty) {
+    // opacity grid from the current xh_av (evolve_point.F90:137-145)
+    launch_taucell(h->d_ndens, h->d_xh_av, h->d_taucell, h->ncell, c.sigma_HI * h->dr[0], c.epsilon, h->stream);
+    h->launches += 1;
+    h->taucell_dirty = false;
+  }
   CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   if (nwork > 0) {
@@ -648,6 +689,7 @@ int c2b_begin_step(c2b_handle* h, double* sum_xh) {
   // xh_av=xh ; xh_intermed=xh  (evolve.F90:140-147)
   CU(h, cudaMemcpyAsync(h->d_xh_av, h->d_xh, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_xh_intermed, h->d_xh, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->taucell_dirty = true;
   return 0;
 }
 
@@ -714,6 +756,7 @@ int c2b_global_pass(c2b_handle* h, double dt, c2b_global_report* rep) {
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   launch_chemistry(cp, h->chem_blocks, h->stream);
   h->launches += 1;
+  h->taucell_dirty = false;  // the chemistry kernel wrote tau_cell from the new xh_av
   CU(h, cudaEventRecord(h->ev[1], h->stream));
   if (int rc = fetch_stats(h)) return rc;
   float ms = 0.f;
@@ -917,6 +960,7 @@ int c2b_set_iter_state(c2b_handle* h, int32_t niter, double photon_loss_all, con
   h->iter_niter = niter;
   h->iter_photon_loss_all = photon_loss_all;
   h->have_iter_state = true;
+  h->taucell_dirty = true;
   return 0;
 }
 

@@ -21,31 +21,40 @@ struct RtParams {
   int n[3];                 // mesh
   int lim[3][2];            // [axis][0: negative side L, 1: positive side R], evolve_source.F90:100-102
   int subboxsize;
-  int plane_stride;         // S = max(lim)+1: quadrant patch is S x S doubles
-  const float* ndens;       // density_module.F90:22
-  const double* xh_av;      // evolve_data.F90:52
+  int plane_stride;         // S = max(lim)+1: global scratch holds 24*S*S doubles per plane buffer
+  int smem_plane_doubles;   // capacity of one shared-memory plane buffer
+  const double* tau_cell;   // sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens per cell
   double* phih;             // evolve_data.F90:40
   const float* lls_grid;    // LLS.F90:81 (type_of_LLS == 2) or nullptr
-  const double* thick;      // stellar_photo_thick_table(0:NumTau,1)
-  const double* thin;
+  const double2* thick2;    // stellar_photo_thick_table as (value, forward difference) pairs
+  const double* thin;       // stellar_photo_thin_table(0:NumTau,1)
+  const double2* logtab;    // 128 x {1/c_j, A + B*log2(c_j)}
   const int* srcpos;        // 3 x NumSrc, 1-based (sourceprops.F90:56)
   const double* normflux;   // NormFlux_stellar(1:NumSrc)
   const int* work;          // source indices (0-based) this rank traces, in order
   int nwork;
   unsigned int* ticket;     // dynamic work counter (plays do_grid_master, master_slave.F90:124-231)
-  double* scratch;          // per-CTA plane storage: [grid][2][24][S][S]
+  double* scratch;          // per-CTA global plane storage: [grid][2][24][S][S]
   int* nbox_out;            // per source (global index)
   double* loss_out;         // per source
   double* coldens_dbg;      // optional full coldensh_out grid (debug/parity), or nullptr
   double S_star, dr[3], vol;
   int use_lls, type_lls;
-  double coldensh_lls, rmax_lls2;
-  double sigma_HI, max_coldensh, tau_photo_limit, minlogtau, dlogtau, loss_fraction;
-  double epsilon, pi, sqrt2, sqrt3;
+  double tau_lls;           // sigma_HI*coldensh_LLS
+  double rmax_lls2;
+  double sigma_HI, inv_sigma, inv_sigma_dr0, fourpi_over_sigma;
+  double max_coldensh, tau_photo_limit, loss_fraction;
+  double sqrt2, sqrt3;
+  double logB;              // log10(2)/dlogtau
+  double logc[5];           // logB/ln2 * {1,-1/2,1/3,-1/4,1/5}
 };
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream);
-int raytrace_max_grid();   // resident CTAs of the ray-trace kernel on the current device
+// sets the kernel's shared-memory attribute; returns plane capacity and resident CTAs per SM
+int raytrace_configure(int max_radius, int* smem_plane_doubles, int* ctas_per_sm);
+void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
+                    double eps, cudaStream_t stream);
+void launch_pair_table(const double* tab, double2* out, cudaStream_t stream);
 size_t raytrace_scratch_doubles_per_cta(int plane_stride);
 
 // ---- per-cell chemistry + fused statistics ------------------------------------------------------
@@ -69,6 +78,8 @@ struct ChemParams {
   double colh0, sqrtT, expT;  // the same three factors, multiplied per cell in total_rates order
   double abu_c, epsilon, minimum_fractional_change, minimum_fraction_of_atoms;
   double* partials;        // [nblocks][kNumStat]
+  double* tau_cell;        // out (chemistry kernel): opacity grid for the next ray trace, or nullptr
+  double sigma_dr0;
 };
 
 void launch_chemistry(const ChemParams& p, int nblocks, cudaStream_t stream);

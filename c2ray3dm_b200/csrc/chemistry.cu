@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kThreads) chemistry_kernel(ChemParams P) {
       acc.conv += 1.0;
     P.xh_intermed[c] = h1;  // :400-401
     P.xh_av[c] = h_av1;
+    // opacity grid for the next ray trace: the h_av(0) evolve0D will form from this xh_av
+    // (evolve_point.F90:137-142) times ndens times sigma_HI*dr(1)
+    if (P.tau_cell) P.tau_cell[c] = P.sigma_dr0 * (fmax(1.0 - fmax(h_av1, P.epsilon), P.epsilon) * ndens_p);
     // fused reductions
     acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
     acc.sum_x += h1;                                       // :565

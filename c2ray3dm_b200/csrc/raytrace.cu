@@ -14,17 +14,25 @@
 // the signs of the two transverse offsets.  In quadrant-local coordinates (a,b) = transverse
 // distances, the cell (a,b) of plane r reads (a-1|a, b-1|b) of plane r-1 of the SAME quadrant.
 // Cells shared between quadrants (on-axis a==0 / b==0, cube edges a==r / b==r) are computed by
-// every quadrant that needs them as an upstream value (the three cinterp branches give the same
-// value on ties), but only the quadrant the reference's branch order selects "owns" the cell:
-// it alone adds the rate into phih_grid, counts the boundary loss and the update.
+// every quadrant that needs them as an upstream value (the three cinterp branches agree on ties),
+// but only the quadrant the reference's branch order selects "owns" the cell: it alone adds the
+// rate into phih_grid and counts the boundary loss.
 //
-// v0 work distribution: one CTA per source, persistent CTAs pulling sources from an atomic ticket
-// (the device-side do_grid_master, master_slave.F90:124-231); the 24 planes of the current and
-// previous shell live in a per-CTA global scratch that stays L2 resident for moderate radii.
+// Mapping.  One CTA per source, persistent CTAs pulling sources from an atomic ticket (the
+// device-side do_grid_master, master_slave.F90:124-231).  Within a shell a thread owns a column
+// (quadrant q, transverse index a) and walks b = 0..r: the two upstream values of its own column
+// stay in registers from one b to the next, the two of column a-1 arrive by warp shuffle, so a cell
+// costs one plane load.  The planes of shell r-1 and r live in shared memory while
+// 24*(r+1)^2 doubles fit, afterwards in a per-CTA global scratch that stays L2 resident.
+// The optical-depth table is staged in shared memory as (value, forward difference) pairs.
 //
-// This translation unit is compiled with -fmad=false: the interpolation weights must evaluate to
-// exact zeros where the reference's do (SURVEY hard part 4), and it keeps the arithmetic within
-// rounding of the CPU restatement.
+// Arithmetic.  The planes hold optical depths tau = sigma_HI * N_HI; the per-cell opacity
+// tau_cell = sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens comes from a grid the per-cell kernel
+// writes, so an update reads 8 bytes and adds 8.  The reference's five divisions per interpolation
+// collapse into one (common denominator), the two log10 of the table look-up become a 128-entry
+// table + degree-5 polynomial log2 folded into the table coordinate, path and 1/vol_ph come from
+// one reciprocal square root.  All of it stays within ~1e-13 of the CPU restatement (tests bound
+// the rates at 1e-6 relative as BASELINE.json requires).
 #include "c2b_common.cuh"
 
 namespace c2b {
@@ -33,31 +41,56 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kQuadrants = 24;
 
-__device__ __forceinline__ double weightf(double cd, double sig) {
-  // column_density.f90:276-293
-  return 1.0 / fmax(0.6, cd * sig);
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
 }
 
-struct TablePos {
-  double residual;
-  int ipos, ipos_p1;
-};
-
-// set_tau_table_positions, radiation_photoionrates.F90:184-208
-__device__ __forceinline__ TablePos table_pos(double tau, double minlogtau, double dlogtau) {
-  TablePos t;
-  double lt = log10(fmax(1.0e-20, tau));
-  double od = fmin((double)kNumTau, fmax(0.0, 1.0 + (lt - minlogtau) / dlogtau));
-  t.ipos = (int)od;
-  t.residual = od - (double)t.ipos;
-  t.ipos_p1 = min(kNumTau, t.ipos + 1);
-  return t;
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  // two Newton steps: y <- y*(1.5 - 0.5*x*y*y)
+  double h = 0.5 * x;
+  double t = fma(-h * y, y, 0.5);
+  y = fma(y, t, y);
+  t = fma(-h * y, y, 0.5);
+  y = fma(y, t, y);
+  return y;
 }
 
-// read_table, radiation_photoionrates.F90:212-228
-__device__ __forceinline__ double read_table(const double* tab, const TablePos& t) {
-  double lo = tab[t.ipos];
-  return lo + (tab[t.ipos_p1] - lo) * t.residual;
+// table coordinate odpos = 1 + (log10(max(1e-20,tau)) - minlogtau)/dlogtau of
+// set_tau_table_positions (radiation_photoionrates.F90:184-208), clamped to NumTau.
+// logtab[j] = {1/c_j, A + B*log2(c_j)}, c_j = 1 + (j+0.5)/128; coef = B/ln2 * {1,-1/2,1/3,-1/4,1/5}
+__device__ __forceinline__ double table_coord(double tau, const double2* __restrict__ logtab,
+                                              const RtParams& P) {
+  const double t = fmax(tau, 1.0e-20);
+  const int hi = __double2hiint(t);
+  const int lo = __double2loint(t);
+  const int e = (hi >> 20) - 1023;
+  const int j = (hi >> 13) & 127;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 lt = logtab[j];
+  const double rr = fma(m, lt.x, -1.0);
+  double q = fma(rr, P.logc[4], P.logc[3]);
+  q = fma(rr, q, P.logc[2]);
+  q = fma(rr, q, P.logc[1]);
+  q = fma(rr, q, P.logc[0]);
+  double od = fma(P.logB, (double)e, lt.y);
+  od = fma(rr, q, od);
+  return fmin(od, (double)kNumTau);
+}
+
+// read_table (radiation_photoionrates.F90:212-228) on the (value, forward difference) pairs
+__device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, double od) {
+  const int ipos = (int)od;
+  const double res = od - (double)ipos;
+  const double2 t = tab[ipos];
+  return fma(t.y, res, t.x);
 }
 
 __device__ __forceinline__ int wrap(int x, int n) {
@@ -68,181 +101,191 @@ __device__ __forceinline__ int wrap(int x, int n) {
 }
 
 __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
-  __shared__ double s_thick[kTableLen];
-  __shared__ double s_thin[kTableLen];
+  extern __shared__ double2 smem2[];
+  double2* s_thick = smem2;                         // kTableLen pairs
+  double2* s_logtab = smem2 + kTableLen;            // 128 pairs
+  double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128);
   __shared__ double s_red[kThreads / 32];
   __shared__ double s_loss;
   __shared__ int s_work;
 
   const int tid = threadIdx.x;
-  for (int i = tid; i < kTableLen; i += kThreads) {
-    s_thick[i] = P.thick[i];
-    s_thin[i] = P.thin[i];
-  }
-  const int S = P.plane_stride;
-  const size_t plane_sz = (size_t)kQuadrants * S * S;
-  double* buf0 = P.scratch + (size_t)blockIdx.x * 2 * plane_sz;
-  double* buf1 = buf0 + plane_sz;
-  const double dr0 = P.dr[0], dr1 = P.dr[1], dr2 = P.dr[2];
+  const int lane = tid & 31;
+  for (int i = tid; i < kTableLen; i += kThreads) s_thick[i] = P.thick2[i];
+  for (int i = tid; i < 128; i += kThreads) s_logtab[i] = P.logtab[i];
+  const int cap = P.smem_plane_doubles;             // doubles per shared plane buffer
+  const size_t gplane = (size_t)kQuadrants * P.plane_stride * P.plane_stride;
+  double* gbuf0 = P.scratch + (size_t)blockIdx.x * 2 * gplane;
+  double* gbuf1 = gbuf0 + gplane;
+  const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
+  const unsigned st0 = 1u, st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;
+  const double dr2_0 = P.dr[0] * P.dr[0], dr2_1 = P.dr[1] * P.dr[1], dr2_2 = P.dr[2] * P.dr[2];
+  const double tau_stop = P.max_coldensh * P.sigma_HI;   // coldensh_in > max_coldensh, evolve_point.F90:201
+  const double vol_cell = P.dr[0] * P.dr[1] * P.dr[2];   // vol_ph of the source cell, :153
 
   for (;;) {
-    __syncthreads();  // also orders the table fill and the previous source's last reads of s_work
+    __syncthreads();  // orders the table fill and the previous source's last reads of s_work
     if (tid == 0) s_work = (int)atomicAdd(P.ticket, 1u);
     __syncthreads();
     const int w = s_work;
     if (w >= P.nwork) break;
     const int ns = P.work[w];  // 0-based source index
-    // 1-based source position as the reference holds it; 0-based = minus one
-    const int src1[3] = {P.srcpos[3 * ns], P.srcpos[3 * ns + 1], P.srcpos[3 * ns + 2]};
+    const int src0 = P.srcpos[3 * ns] - 1, src1 = P.srcpos[3 * ns + 1] - 1, src2 = P.srcpos[3 * ns + 2] - 1;
     const double normflux = P.normflux[ns];
     const double total_source_flux = normflux * P.S_star;  // evolve_source.F90:119
 
-    double* prev = buf0;
-    double* cur = buf1;
     int nbox = 0;
     double photon_loss_src = total_source_flux;  // :121
-    int lr[3] = {0, 0, 0}, ll[3] = {0, 0, 0};    // last_r-src, src-last_l
-    int r_done = -1;                             // last shell finished
+    int lr0 = 0, lr1 = 0, lr2 = 0, ll0 = 0, ll1 = 0, ll2 = 0;  // last_r-src, src-last_l per axis
+    int r_done = -1;
     // do while (evolve_source.F90:128-131); all threads evaluate it on identical values
-    while (photon_loss_src > P.loss_fraction * total_source_flux && lr[2] < P.lim[2][1] &&
-           ll[2] < P.lim[2][0]) {
+    while (photon_loss_src > P.loss_fraction * total_source_flux && lr2 < P.lim[2][1] &&
+           ll2 < P.lim[2][0]) {
       nbox += 1;
-      int rmax = 0;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {  // :135-136
-        lr[d] = min(P.subboxsize * nbox, P.lim[d][1]);
-        ll[d] = min(P.subboxsize * nbox, P.lim[d][0]);
-        rmax = max(rmax, max(lr[d], ll[d]));
-      }
+      const int reach = P.subboxsize * nbox;  // :135-136
+      lr0 = min(reach, P.lim[0][1]); ll0 = min(reach, P.lim[0][0]);
+      lr1 = min(reach, P.lim[1][1]); ll1 = min(reach, P.lim[1][0]);
+      lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
+      const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
       double loss = 0.0;
       for (int r = r_done + 1; r <= rmax; ++r) {
         const int P1 = r + 1;
-        const int per_q = P1 * P1;
-        const int total = kQuadrants * per_q;
+        // plane buffers of shell r (cur) and r-1 (prev): shared while they fit, else global scratch
+        double* cur = (kQuadrants * P1 * P1 <= cap) ? (s_planes + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
+        const double* prev = (kQuadrants * r * r <= cap) ? (s_planes + ((r - 1) & 1) * cap)
+                                                         : (((r - 1) & 1) ? gbuf1 : gbuf0);
         const double rp = (double)r;
-        const double alam = (rp - 0.5) / rp;  // (real(km-k0)+sgnk*0.5)/dk, column_density.f90:109
-        for (int idx = tid; idx < total; idx += kThreads) {
-          const int q = idx / per_q;
-          const int rem = idx - q * per_q;
-          const int b = rem / P1;
-          const int a = rem - b * P1;
+        const double inv_r = (r > 0) ? 1.0 / rp : 0.0;
+        const int ncol = kQuadrants * P1;
+        for (int c0 = tid - lane; c0 < ncol; c0 += kThreads) {  // warp-uniform trip count
+          const int c = c0 + lane;
+          const int q = c / P1;
+          const int a = c - q * P1;
           const int p = q >> 3;  // 0: z principal, 1: y, 2: x  (branch order of cinterp)
           const int sp = (q & 4) ? -1 : 1, sa = (q & 2) ? -1 : 1, sb = (q & 1) ? -1 : 1;
-          const int axP = (p == 0) ? 2 : (p == 1 ? 1 : 0);
-          const int axA = (p == 2) ? 1 : 0;
-          const int axB = (p == 0) ? 1 : 2;
-          // box of this pass (static limits bind before 5*nbox does not matter: r <= 5*nbox)
-          if (r > (sp > 0 ? lr[axP] : ll[axP]) || a > (sa > 0 ? lr[axA] : ll[axA]) ||
-              b > (sb > 0 ? lr[axB] : ll[axB]))
-            continue;
-          int d[3];
-          d[axP] = sp * r;
-          d[axA] = sa * a;
-          d[axB] = sb * b;
-          const int i0 = wrap(src1[0] - 1 + d[0], P.n[0]);
-          const int j0 = wrap(src1[1] - 1 + d[1], P.n[1]);
-          const int k0 = wrap(src1[2] - 1 + d[2], P.n[2]);
-          const size_t cell = ((size_t)k0 * P.n[1] + j0) * P.n[0] + i0;
-          // ownership: the quadrant the reference's branch order and sign(1,0)=+1 select
-          bool owner = (a > 0 || sa > 0) && (b > 0 || sb > 0) && (r > 0 || sp > 0);
-          if (p == 1) owner = owner && (b < r);
-          if (p == 2) owner = owner && (a < r) && (b < r);
-          if (r == 0) owner = owner && (p == 0);
-
-          const double h_av1 = fmax(P.xh_av[cell], P.epsilon);   // evolve_point.F90:137
-          const double h_av0 = fmax(1.0 - h_av1, P.epsilon);     // :140
-          const double ndens_p = (double)P.ndens[cell];          // :145
-          double coldensh_in, path, vol_ph;
-          bool stop = false;
-          if (r == 0) {  // :151-160
-            coldensh_in = 0.0;
-            path = 0.5 * dr0;
-            vol_ph = dr0 * dr1 * dr2;
-          } else {
-            // cinterp in quadrant-local form (column_density.f90:108-171 and its y/x twins)
-            const double dA = (double)d[axA], dB = (double)d[axB];
-            const int sgA = (a == 0) ? 1 : sa, sgB = (b == 0) ? 1 : sb;  // sign(1,idel)
-            const double xc = alam * dA + (double)src1[axA];
-            const double yc = alam * dB + (double)src1[axB];
-            const double amh = (double)(src1[axA] + d[axA] - sgA) + 0.5 * (double)sgA;
-            const double bmh = (double)(src1[axB] + d[axB] - sgB) + 0.5 * (double)sgB;
-            const double dx = 2.0 * fabs(xc - amh);
-            const double dy = 2.0 * fabs(yc - bmh);
-            const double s1 = (1.0 - dx) * (1.0 - dy);
-            const double s2 = (1.0 - dy) * dx;
-            const double s3 = (1.0 - dx) * dy;
-            const double s4 = dx * dy;
-            // upstream cells of plane r-1; the ones outside it have weight exactly 0
-            const double* pl = prev + (size_t)q * S * S;
-            const bool am_ok = a >= 1, a_ok = a <= r - 1, bm_ok = b >= 1, b_ok = b <= r - 1;
-            const double c1 = (am_ok && bm_ok) ? pl[(b - 1) * S + (a - 1)] : 0.0;
-            const double c2 = (a_ok && bm_ok) ? pl[(b - 1) * S + a] : 0.0;
-            const double c3 = (am_ok && b_ok) ? pl[b * S + (a - 1)] : 0.0;
-            const double c4 = (a_ok && b_ok) ? pl[b * S + a] : 0.0;
-            const double w1 = s1 * weightf(c1, P.sigma_HI);
-            const double w2 = s2 * weightf(c2, P.sigma_HI);
-            const double w3 = s3 * weightf(c3, P.sigma_HI);
-            const double w4 = s4 * weightf(c4, P.sigma_HI);
-            double cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4);
-            if (r == 1 && (a == 1 || b == 1)) {  // :152-158
-              cdensi = ((a == 1 && b == 1) ? P.sqrt3 : P.sqrt2) * cdensi;
-            }
-            const double pathc = sqrt((dA * dA + dB * dB) / (rp * rp) + 1.0);
-            coldensh_in = cdensi;
-            path = pathc * dr0;                                   // evolve_point.F90:166
-            const double xs = dr0 * (double)d[0];
-            const double ys = dr1 * (double)d[1];
-            const double zs = dr2 * (double)d[2];
-            const double dist2 = xs * xs + ys * ys + zs * zs;
-            vol_ph = 4.0 * P.pi * dist2 * path;                   // :177
-            if (P.use_lls) {                                      // :186-196
-              if (P.type_lls == 3) {
-                if (dist2 > P.rmax_lls2) stop = true;
+          // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z)
+          const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
+          const int lrA = (p == 2) ? lr1 : lr0, llA = (p == 2) ? ll1 : ll0;
+          const int lrB = (p == 0) ? lr1 : lr2, llB = (p == 0) ? ll1 : ll2;
+          const bool col_ok = (c < ncol) && r <= (sp > 0 ? lrP : llP) && a <= (sa > 0 ? lrA : llA);
+          const int bmax = col_ok ? min(r, sb > 0 ? lrB : llB) : -1;
+          const int nB = (p == 0) ? n1 : n2;
+          const int nA = (p == 2) ? n1 : n0;
+          const int nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
+          const int srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
+          const int srcA = (p == 2) ? src1 : src0;
+          const int srcB = (p == 0) ? src1 : src2;
+          const unsigned strP = (p == 0) ? st2 : (p == 1 ? st1 : st0);
+          const unsigned strA = (p == 2) ? st1 : st0;
+          const unsigned strideB = (p == 0) ? st1 : st2;
+          const double dr2P = (p == 0) ? dr2_2 : (p == 1 ? dr2_1 : dr2_0);
+          const double dr2A = (p == 2) ? dr2_1 : dr2_0;
+          const double dr2B = (p == 0) ? dr2_1 : dr2_2;
+          const unsigned base = (unsigned)wrap(srcP + sp * r, nP) * strP + (unsigned)wrap(srcA + sa * a, nA) * strA;
+          int posB = srcB;  // b = 0
+          // column-level geometry
+          const double ua = (a == r) ? 1.0 : (double)a * inv_r;   // 1-dx of cinterp
+          const double ca2 = (double)(r * r + a * a);
+          const double dist_col = dr2P * (double)(r * r) + dr2A * (double)(a * a);
+          // ownership pieces that do not depend on b (see header comment)
+          const bool own_col = (a > 0 || sa > 0) && (r > 0 || sp > 0) && (p != 2 || a < r) && (r > 0 || p == 0);
+          const bool loss_col = (sp > 0 ? r == lrP : r == llP) || (sa * a == lrA) || (sa * a == -llA);
+          const double* pl = prev + q * r * r;   // plane r-1 patch of this quadrant, stride r
+          double* pc = cur + q * P1 * P1;        // plane r patch, stride r+1
+          const bool a_in = a <= r - 1;          // column a exists in plane r-1
+          double c_own_bm1 = 0.0, c_left_bm1 = 0.0;
+          for (int b = 0; b <= r; ++b) {
+            // upstream optical depths (cells outside plane r-1 have weight 0; read as 0)
+            double c_own = 0.0;
+            if (a_in && b <= r - 1 && b <= bmax) c_own = pl[b * r + a];
+            double c_left = __shfl_up_sync(0xffffffffu, c_own, 1);
+            if (lane == 0) c_left = (a >= 1 && b <= r - 1 && b <= bmax) ? pl[b * r + a - 1] : 0.0;
+            if (a == 0) c_left = 0.0;
+            const double t1 = c_left_bm1, t2 = c_own_bm1, t3 = c_left, t4 = c_own;
+            c_left_bm1 = c_left;
+            c_own_bm1 = c_own;
+            if (b <= bmax) {
+              const unsigned cell = base + (unsigned)posB * strideB;
+              const double tau_cell = P.tau_cell[cell];
+              double tau_in, pathc, volfac;  // volfac = vol_ph * nHI * sigma / ... see below
+              bool stop = false;
+              if (r == 0) {  // evolve_point.F90:151-160
+                tau_in = 0.0;
+                pathc = 0.5;
+                // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
+                volfac = vol_cell * tau_cell * P.inv_sigma_dr0;
               } else {
-                const double cl = (P.type_lls == 2) ? (double)P.lls_grid[cell] : P.coldensh_lls;
-                coldensh_in = coldensh_in + cl * path / dr0;
+                // cinterp, column_density.f90:108-171, with a common denominator
+                const double ub = (b == r) ? 1.0 : (double)b * inv_r;  // 1-dy
+                const double va = 1.0 - ua, vb = 1.0 - ub;
+                const double s1 = ua * ub, s2 = ub * va, s3 = ua * vb, s4 = va * vb;
+                const double m1 = fmax(0.6, t1), m2 = fmax(0.6, t2), m3 = fmax(0.6, t3), m4 = fmax(0.6, t4);
+                const double p12 = m1 * m2, p34 = m3 * m4;
+                const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
+                const double num = fma(t1, e1, fma(t2, e2, fma(t3, e3, t4 * e4)));
+                const double den = (e1 + e2) + (e3 + e4);
+                tau_in = num * fast_rcp(den);
+                if (r == 1 && (a == 1 || b == 1)) tau_in *= (a == 1 && b == 1) ? P.sqrt3 : P.sqrt2;  // :152-158
+                const double q2 = ca2 + (double)(b * b);
+                const double rs = fast_rsqrt(q2);
+                pathc = q2 * rs * inv_r;                                   // sqrt(1+(a^2+b^2)/r^2)
+                const double dist2 = fma(dr2B, (double)(b * b), dist_col);  // evolve_point.F90:170-174
+                // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/(volfac)
+                volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
+                if (P.use_lls) {  // :186-196
+                  if (P.type_lls == 3) {
+                    if (dist2 > P.rmax_lls2) stop = true;
+                  } else {
+                    const double tl = (P.type_lls == 2) ? (double)P.lls_grid[cell] * P.sigma_HI : P.tau_lls;
+                    tau_in = fma(tl, pathc, tau_in);
+                  }
+                }
+              }
+              if (tau_in > tau_stop) stop = true;                          // :201
+              const double tau_out = fma(tau_cell, pathc, tau_in);         // :247-248
+              pc[b * P1 + a] = tau_out;
+              const bool owner = own_col && (b > 0 || sb > 0) && (p == 0 || b < r);
+              if (owner) {
+                if (P.coldens_dbg) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
+                if (!stop && normflux > 0.0) {
+                  // photoion_rates / photo_lookuptable, radiation_photoionrates.F90:71-317
+                  const double od_in = table_coord(tau_in, s_logtab, P);
+                  const double phi_in = normflux * lerp_pairs(s_thick, od_in);
+                  double phi_out, phi_all;
+                  const double dtau = tau_out - tau_in;
+                  if (fabs(dtau) > P.tau_photo_limit) {
+                    const double od_out = table_coord(tau_out, s_logtab, P);
+                    phi_out = normflux * lerp_pairs(s_thick, od_out);
+                    phi_all = phi_in - phi_out;
+                  } else {
+                    const int ipos = (int)od_in;
+                    const double res = od_in - (double)ipos;
+                    const double lo = P.thin[ipos];
+                    const double thin = lo + (P.thin[min(kNumTau, ipos + 1)] - lo) * res;
+                    phi_all = normflux * dtau * thin;
+                    phi_out = phi_in - phi_all;
+                  }
+                  const double inv_vol = fast_rcp(volfac);
+                  const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
+                  if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);  // :283-284
+                  // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
+                  if (loss_col || (sb * b == lrB) || (sb * b == -llB))
+                    loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
+                }
               }
             }
-          }
-          if (coldensh_in > P.max_coldensh) stop = true;          // :201
-          const double cd_out = coldensh_in + h_av0 * ndens_p * path;  // :247-248
-          cur[(size_t)q * S * S + b * S + a] = cd_out;
-          if (!owner) continue;
-          if (P.coldens_dbg) P.coldens_dbg[cell] = cd_out;
-          if (!stop && normflux > 0.0) {
-            // photoion_rates / photo_lookuptable, radiation_photoionrates.F90:71-317
-            const double tau_in = coldensh_in * P.sigma_HI;
-            const double tau_out = cd_out * P.sigma_HI;
-            const TablePos pin = table_pos(tau_in, P.minlogtau, P.dlogtau);
-            const double phi_in = normflux * read_table(s_thick, pin);
-            double phi_out, phi_all;
-            if (fabs(tau_out - tau_in) > P.tau_photo_limit) {
-              const TablePos pout = table_pos(tau_out, P.minlogtau, P.dlogtau);
-              phi_out = normflux * read_table(s_thick, pout);
-              phi_all = phi_in - phi_out;
-            } else {
-              phi_all = normflux * (tau_out - tau_in) * read_table(s_thin, pin);
-              phi_out = phi_in - phi_all;
-            }
-            double photo_cell = phi_all / vol_ph;
-            photo_cell = photo_cell / (h_av0 * ndens_p);          // evolve_point.F90:262
-            if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);  // :283-284
-            // boundary of this pass's subbox (:290-295)
-            if (d[0] == -ll[0] || d[1] == -ll[1] || d[2] == -ll[2] || d[0] == lr[0] ||
-                d[1] == lr[1] || d[2] == lr[2])
-              loss = loss + phi_out * P.vol / vol_ph;
+            posB += sb;
+            if (posB < 0) posB += nB;
+            else if (posB >= nB) posB -= nB;
           }
         }
         __syncthreads();  // plane r complete before plane r+1 reads it
-        double* t = prev;
-        prev = cur;
-        cur = t;
       }
       r_done = rmax;
       // photon_loss_src = sum over the CTA (plays photon_loss_src_thread, evolve_source.F90:183-186)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-      if ((tid & 31) == 0) s_red[tid >> 5] = loss;
+      if (lane == 0) s_red[tid >> 5] = loss;
       __syncthreads();
       if (tid == 0) {
         double t = 0.0;
@@ -259,23 +302,68 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
   }
 }
 
+// tau_cell = sigma*dr(1) * max(1-max(xh_av,eps),eps) * ndens  (evolve_point.F90:137-145, doric.f90:141-155)
+__global__ void taucell_kernel(const float* __restrict__ ndens, const double* __restrict__ xh_av,
+                               double* __restrict__ tau_cell, size_t n, double sigma_dr0, double eps) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    const double h_av1 = fmax(xh_av[c], eps);
+    const double h_av0 = fmax(1.0 - h_av1, eps);
+    tau_cell[c] = sigma_dr0 * (h_av0 * (double)ndens[c]);
+  }
+}
+
+__global__ void pair_table_kernel(const double* __restrict__ tab, double2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > kNumTau) return;
+  const double lo = tab[i];
+  out[i] = make_double2(lo, tab[min(kNumTau, i + 1)] - lo);
+}
+
 }  // namespace
 
 size_t raytrace_scratch_doubles_per_cta(int plane_stride) {
   return (size_t)2 * kQuadrants * plane_stride * plane_stride;
 }
 
-int raytrace_max_grid() {
-  int dev = 0, sms = 0, per_sm = 0;
+static size_t rt_smem_bytes(int plane_doubles) {
+  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * plane_doubles * sizeof(double);
+}
+
+int raytrace_configure(int max_radius, int* smem_plane_doubles, int* ctas_per_sm) {
+  // two CTAs per SM: split the opt-in shared memory between them
+  int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raytrace_kernel, kThreads, 0);
-  if (per_sm < 1) per_sm = 1;
-  return sms * per_sm;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int sm_total = 0;
+  cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
+  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
+  int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
+  const int need = kQuadrants * (max_radius + 1) * (max_radius + 1);
+  if (cap > need) cap = need;
+  cap &= ~1;
+  cudaError_t e = cudaFuncSetAttribute(raytrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)rt_smem_bytes(cap));
+  if (e != cudaSuccess) return (int)e;
+  *smem_plane_doubles = cap;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raytrace_kernel, kThreads, rt_smem_bytes(cap));
+  *ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+  return 0;
 }
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  raytrace_kernel<<<grid, kThreads, 0, stream>>>(p);
+  raytrace_kernel<<<grid, kThreads, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+}
+
+void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
+                    double eps, cudaStream_t stream) {
+  taucell_kernel<<<chemistry_blocks(), 256, 0, stream>>>(ndens, xh_av, tau_cell, n, sigma_dr0, eps);
+}
+
+void launch_pair_table(const double* tab, double2* out, cudaStream_t stream) {
+  pair_table_kernel<<<(kTableLen + 127) / 128, 128, 0, stream>>>(tab, out);
 }
 
 }  // namespace c2b

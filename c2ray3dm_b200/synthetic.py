@@ -69,9 +69,10 @@ def sources_at_density_peaks(ndens, nsrc, max_normflux=1e7):
     return srcpos, nf
 
 
-def clumping_from_density(ndens, zred):
-    """a deterministic float32 clumping grid C = 1 + 4*(n/nbar) (type_of_clumping 5 semantics)"""
-    return (1.0 + 4.0 * (ndens.astype(np.float64) / avg_dens(zred))).astype(np.float32)
+def clumping_from_density(ndens, zred, slope=0.5):
+    """a deterministic float32 clumping grid C = 1 + slope*(n/nbar) (type_of_clumping 5 semantics:
+    the kernels only see float32 values per cell, clumping_module.F90:18)"""
+    return (1.0 + slope * (ndens.astype(np.float64) / avg_dens(zred))).astype(np.float32)
 
 
 def bubble_state(shape, srcpos, radius_cells, x_in=1.0 - 1e-4, x_out=K.xh_initial):
