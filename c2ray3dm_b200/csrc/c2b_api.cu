@@ -5,8 +5,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -66,7 +68,10 @@ struct c2b_handle {
   double *d_thick = nullptr, *d_thin = nullptr, *d_taucell = nullptr;
   double2 *d_thick2 = nullptr, *d_logtab = nullptr;
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
-  int smem_plane_doubles = 0;
+  RtLaunchInfo rt;             // shared-memory plane capacities and resident grid sizes
+  int* d_work2 = nullptr;      // work list of the cluster kernel
+  std::vector<int> nbox_pred;  // per source: nbox of the previous trace (routing + longest-first order)
+  int cluster_min_nbox = 3;    // sources predicted to need >= this many subboxes go to the cluster kernel
   bool have_tables = false, have_density = false, have_xh = false, have_geometry = false;
   // sources
   int NumSrc = 0, nwork = 0;
@@ -255,7 +260,7 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMemsetAsync(h->d_phih, 0, n * sizeof(double), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMalloc(&h->d_thick, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&h->d_ticket, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMalloc(&h->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_taucell, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell", e);
   if ((e = cudaMalloc(&h->d_thick2, kTableLen * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_logtab, 128 * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -278,10 +283,9 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
     smax = std::max(smax, std::max(h->lim[d][0], h->lim[d][1]));
   }
   h->plane_stride = smax + 1;
-  int per_sm = 1, sms = 0;
-  if (raytrace_configure(smax, &h->smem_plane_doubles, &per_sm)) return bail("raytrace_configure", cudaGetLastError());
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-  h->rt_grid = sms * per_sm;
+  if (raytrace_configure(smax, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
+  h->rt_grid = h->rt.grid_max;
+  if (const char* env = getenv("C2B_CLUSTER_MIN_NBOX")) h->cluster_min_nbox = atoi(env);
   const size_t scratch = raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt_grid;
   if ((e = cudaMalloc(&h->d_scratch, scratch * sizeof(double))) != cudaSuccess) return bail("cudaMalloc scratch", e);
   h->chem_blocks = chemistry_blocks();
@@ -304,7 +308,7 @@ void c2b_destroy(c2b_handle* h) {
   cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
   cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
-  cudaFree(h->d_work); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
+  cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -474,7 +478,8 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
       if (srcpos[3 * s + d] < 1 || srcpos[3 * s + d] > h->cfg.mesh[d])
         return fail(h, "c2b_set_sources: source position outside the mesh (positions are 1-based)");
   if (bind_device(h)) return 1;
-  cudaFree(h->d_srcpos); cudaFree(h->d_normflux); cudaFree(h->d_work); cudaFree(h->d_nbox); cudaFree(h->d_loss);
+  cudaFree(h->d_srcpos); cudaFree(h->d_normflux); cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss);
+  h->d_work2 = nullptr;
   h->d_srcpos = nullptr; h->d_normflux = nullptr; h->d_work = nullptr; h->d_nbox = nullptr; h->d_loss = nullptr;
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -486,6 +491,7 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   // do ns1=1+rank,NumSrc,npr (master_slave.F90:85)
   for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
   h->nwork = (int)h->work.size();
+  h->nbox_pred.assign((size_t)NumSrc, 0);
   h->sum_normflux = 0.0;
   for (int s = 0; s < NumSrc; ++s) h->sum_normflux = h->sum_normflux + nf[s];  // sum(NormFlux_stellar(1:NumSrc))
   if (NumSrc == 0) return 0;
@@ -493,6 +499,7 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   CU(h, cudaMalloc(&h->d_srcpos, 3 * ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_normflux, ns * sizeof(double)));
   CU(h, cudaMalloc(&h->d_work, std::max<size_t>(1, h->work.size()) * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_work2, std::max<size_t>(1, h->work.size()) * sizeof(int)));
   CU(h, cudaMalloc(&h->d_nbox, ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_loss, ns * sizeof(double)));
   CU(h, cudaMallocHost(&h->h_nbox, ns * sizeof(int)));
@@ -591,7 +598,9 @@ static void absorb_after(c2b_handle* h, double dt) {
   h->total_ion = h->totrec + h->dh0;
 }
 
-static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* coldens_dbg, float* ms) {
+// traces the sources of d_work (one CTA each) and of d_work_cl (one cluster of 8 CTAs each)
+static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int* d_work_cl, int nwork_cl,
+                         double* coldens_dbg, float* ms) {
   const c2b_config& c = h->cfg;
   RtParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -603,7 +612,8 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* co
   }
   rp.subboxsize = c.subboxsize;
   rp.plane_stride = h->plane_stride;
-  rp.smem_plane_doubles = h->smem_plane_doubles;
+  rp.smem_plane_doubles = h->rt.smem_plane_doubles;
+  rp.smem_plane_doubles_cl = h->rt.smem_plane_doubles_cl;
   rp.tau_cell = h->d_taucell;
   rp.phih = h->d_phih;
   rp.lls_grid = h->d_lls;
@@ -645,10 +655,22 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, double* co
     h->launches += 1;
     h->taucell_dirty = false;
   }
-  CU(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+  CU(h, cudaMemsetAsync(h->d_ticket, 0, 2 * sizeof(unsigned int), h->stream));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
+  if (nwork_cl > 0) {  // long traces first: one cluster per source, planes in shared memory
+    RtParams rc = rp;
+    rc.work = d_work_cl;
+    rc.nwork = nwork_cl;
+    rc.ticket = h->d_ticket + 1;
+    const int ncl = std::min(h->rt.clusters, nwork_cl);
+    if (launch_raytrace_cluster(rc, ncl, h->stream)) {
+      CU(h, cudaGetLastError());
+      return fail(h, "cluster launch failed");
+    }
+    h->launches += 1;
+  }
   if (nwork > 0) {
-    const int grid = std::min(h->rt_grid, nwork);
+    const int grid = std::min(h->rt.grid_cta, nwork);
     launch_raytrace(rp, grid, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
@@ -708,12 +730,23 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
   if (h->NumSrc > 0) {
     CU(h, cudaMemsetAsync(h->d_nbox, 0, (size_t)h->NumSrc * sizeof(int), h->stream));
     CU(h, cudaMemsetAsync(h->d_loss, 0, (size_t)h->NumSrc * sizeof(double), h->stream));
-    if (int rc = trace_sources(h, h->d_work, h->nwork, nullptr, &ms_rt)) return rc;
+    // route by the subbox count of the previous trace, longest first (the work queue is dynamic, so
+    // the order only affects load balance and the order of the atomic additions)
+    std::vector<int> small, large;
+    for (int w : h->work) (h->nbox_pred[w] >= h->cluster_min_nbox ? large : small).push_back(w);
+    std::stable_sort(large.begin(), large.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
+    std::stable_sort(small.begin(), small.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
+    if (!small.empty())
+      CU(h, cudaMemcpyAsync(h->d_work, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (!large.empty())
+      CU(h, cudaMemcpyAsync(h->d_work2, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), nullptr, &ms_rt)) return rc;
     CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     // photon_loss(1)=photon_loss(1)+photon_loss_src ; sum_nbox=sum_nbox+nbox, in source order
     for (int w : h->work) {
+      h->nbox_pred[w] = h->h_nbox[w];
       loss_sum = loss_sum + h->h_loss[w];
       nbox_sum += (double)h->h_nbox[w];
       upd_sum += (double)box_updates(h, h->h_nbox[w]);
@@ -996,7 +1029,10 @@ int c2b_trace_source_debug(c2b_handle* h, int32_t ns, double* coldensh_out, doub
   CU(h, cudaMemsetAsync(d_dbg, 0, h->ncell * sizeof(double), h->stream));
   CU(h, cudaMemsetAsync(h->d_phih, 0, h->ncell * sizeof(double), h->stream));
   // the trace reads xh_av; outside evolve3D that is the caller's responsibility (tests copy xh)
-  int rc = trace_sources(h, d_one, 1, d_dbg, nullptr);
+  // C2B_DEBUG_CLUSTER=1 sends the diagnostic trace through the cluster kernel
+  const char* envc = getenv("C2B_DEBUG_CLUSTER");
+  const bool use_cl = envc && atoi(envc) != 0;
+  int rc = use_cl ? trace_sources(h, nullptr, 0, d_one, 1, d_dbg, nullptr) : trace_sources(h, d_one, 1, nullptr, 0, d_dbg, nullptr);
   if (!rc && coldensh_out) rc = download(h, coldensh_out, d_dbg, h->ncell * 8, "coldensh_out");
   if (!rc && phih) rc = download(h, phih, h->d_phih, h->ncell * 8, "phih");
   int nb = 0;

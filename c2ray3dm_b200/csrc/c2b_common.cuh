@@ -22,7 +22,8 @@ struct RtParams {
   int lim[3][2];            // [axis][0: negative side L, 1: positive side R], evolve_source.F90:100-102
   int subboxsize;
   int plane_stride;         // S = max(lim)+1: global scratch holds 24*S*S doubles per plane buffer
-  int smem_plane_doubles;   // capacity of one shared-memory plane buffer
+  int smem_plane_doubles;   // capacity of one shared-memory plane buffer (single-CTA kernel)
+  int smem_plane_doubles_cl;  // same for a CTA of the cluster kernel
   const double* tau_cell;   // sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens per cell
   double* phih;             // evolve_data.F90:40
   const float* lls_grid;    // LLS.F90:81 (type_of_LLS == 2) or nullptr
@@ -50,8 +51,15 @@ struct RtParams {
 };
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream);
-// sets the kernel's shared-memory attribute; returns plane capacity and resident CTAs per SM
-int raytrace_configure(int max_radius, int* smem_plane_doubles, int* ctas_per_sm);
+struct RtLaunchInfo {
+  int smem_plane_doubles, smem_plane_doubles_cl;
+  int grid_cta;    // resident CTAs of the single-CTA kernel
+  int clusters;    // resident clusters of the cluster kernel
+  int grid_max;    // CTAs the scratch must be sized for
+};
+// sets the kernels' shared-memory attributes and queries the resident grid sizes
+int raytrace_configure(int max_radius, RtLaunchInfo* info);
+int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream);
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
                     double eps, cudaStream_t stream);
 void launch_pair_table(const double* tab, double2* out, cudaStream_t stream);

@@ -33,12 +33,18 @@
 // table + degree-5 polynomial log2 folded into the table coordinate, path and 1/vol_ph come from
 // one reciprocal square root.  All of it stays within ~1e-13 of the CPU restatement (tests bound
 // the rates at 1e-6 relative as BASELINE.json requires).
+#include <cooperative_groups.h>
+
 #include "c2b_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace c2b {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreadsCta = 256;   // one CTA per source
+constexpr int kThreadsCl = 512;    // cluster of 8 CTAs per source
+constexpr int kClusterSize = 8;
 constexpr int kQuadrants = 24;
 
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -100,21 +106,29 @@ __device__ __forceinline__ int wrap(int x, int n) {
   return x;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
+// One CTA (kCluster == 1) or one cluster of 8 CTAs (kCluster == 8, one CTA per octant with its three
+// face quadrants) per source.
+template <int kT, int kCluster>
+__global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(RtParams P) {
+  constexpr int kNq = kQuadrants / kCluster;        // face quadrants handled by this CTA
   extern __shared__ double2 smem2[];
   double2* s_thick = smem2;                         // kTableLen pairs
   double2* s_logtab = smem2 + kTableLen;            // 128 pairs
   double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128);
-  __shared__ double s_red[kThreads / 32];
-  __shared__ double s_loss;
+  __shared__ double s_red[kT / 32];
+  __shared__ double s_slot[2][8];                   // per-octant boundary loss, alternating by pass (rank 0's copy is used)
   __shared__ int s_work;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  for (int i = tid; i < kTableLen; i += kThreads) s_thick[i] = P.thick2[i];
-  for (int i = tid; i < 128; i += kThreads) s_logtab[i] = P.logtab[i];
-  const int cap = P.smem_plane_doubles;             // doubles per shared plane buffer
-  const size_t gplane = (size_t)kQuadrants * P.plane_stride * P.plane_stride;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = (kCluster > 1) ? cluster.block_rank() : 0u;
+  const unsigned cid = (kCluster > 1) ? (blockIdx.x / kCluster) : blockIdx.x;   // work-group index
+  (void)cid;
+  for (int i = tid; i < kTableLen; i += kT) s_thick[i] = P.thick2[i];
+  for (int i = tid; i < 128; i += kT) s_logtab[i] = P.logtab[i];
+  const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;  // per shared plane buffer
+  const size_t gplane = (size_t)kNq * P.plane_stride * P.plane_stride;
   double* gbuf0 = P.scratch + (size_t)blockIdx.x * 2 * gplane;
   double* gbuf1 = gbuf0 + gplane;
   const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
@@ -122,12 +136,20 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
   const double dr2_0 = P.dr[0] * P.dr[0], dr2_1 = P.dr[1] * P.dr[1], dr2_2 = P.dr[2] * P.dr[2];
   const double tau_stop = P.max_coldensh * P.sigma_HI;   // coldensh_in > max_coldensh, evolve_point.F90:201
   const double vol_cell = P.dr[0] * P.dr[1] * P.dr[2];   // vol_ph of the source cell, :153
+  int pass_parity = 0;
 
   for (;;) {
-    __syncthreads();  // orders the table fill and the previous source's last reads of s_work
-    if (tid == 0) s_work = (int)atomicAdd(P.ticket, 1u);
+    // ---- next source (device-side do_grid_master: one ticket per work group) ---------------------
     __syncthreads();
-    const int w = s_work;
+    if (crank == 0 && tid == 0) s_work = (int)atomicAdd(P.ticket, 1u);
+    int w;
+    if (kCluster > 1) {
+      cluster.sync();
+      w = *cluster.map_shared_rank(&s_work, 0);
+    } else {
+      __syncthreads();
+      w = s_work;
+    }
     if (w >= P.nwork) break;
     const int ns = P.work[w];  // 0-based source index
     const int src0 = P.srcpos[3 * ns] - 1, src1 = P.srcpos[3 * ns + 1] - 1, src2 = P.srcpos[3 * ns + 2] - 1;
@@ -138,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
     double photon_loss_src = total_source_flux;  // :121
     int lr0 = 0, lr1 = 0, lr2 = 0, ll0 = 0, ll1 = 0, ll2 = 0;  // last_r-src, src-last_l per axis
     int r_done = -1;
-    // do while (evolve_source.F90:128-131); all threads evaluate it on identical values
+    // do while (evolve_source.F90:128-131); every thread of the work group evaluates it on identical values
     while (photon_loss_src > P.loss_fraction * total_source_flux && lr2 < P.lim[2][1] &&
            ll2 < P.lim[2][0]) {
       nbox += 1;
@@ -151,24 +173,43 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
       for (int r = r_done + 1; r <= rmax; ++r) {
         const int P1 = r + 1;
         // plane buffers of shell r (cur) and r-1 (prev): shared while they fit, else global scratch
-        double* cur = (kQuadrants * P1 * P1 <= cap) ? (s_planes + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
-        const double* prev = (kQuadrants * r * r <= cap) ? (s_planes + ((r - 1) & 1) * cap)
-                                                         : (((r - 1) & 1) ? gbuf1 : gbuf0);
-        const double rp = (double)r;
-        const double inv_r = (r > 0) ? 1.0 / rp : 0.0;
-        const int ncol = kQuadrants * P1;
-        for (int c0 = tid - lane; c0 < ncol; c0 += kThreads) {  // warp-uniform trip count
-          const int c = c0 + lane;
-          const int q = c / P1;
-          const int a = c - q * P1;
-          const int p = q >> 3;  // 0: z principal, 1: y, 2: x  (branch order of cinterp)
-          const int sp = (q & 4) ? -1 : 1, sa = (q & 2) ? -1 : 1, sb = (q & 1) ? -1 : 1;
+        double* cur = (kNq * P1 * P1 <= cap) ? (s_planes + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
+        const double* prev = (kNq * r * r <= cap) ? (s_planes + ((r - 1) & 1) * cap)
+                                                  : (((r - 1) & 1) ? gbuf1 : gbuf0);
+        const double inv_r = (r > 0) ? 1.0 / (double)r : 0.0;
+        // work items: (segment of b, quadrant, column a), a fastest so that a warp spans adjacent columns
+        const int ncol = kNq * P1;
+        int nseg = kT / ncol;
+        nseg = max(1, min(nseg, P1 / 2));
+        const int seglen = (P1 + nseg - 1) / nseg;
+        const int nitem = ncol * nseg;
+        for (int it0 = tid - lane; it0 < nitem; it0 += kT) {  // warp-uniform trip count
+          const int it = it0 + lane;
+          const int seg = it / ncol;
+          const int c = it - seg * ncol;
+          const int ql = c / P1;
+          const int a = c - ql * P1;
+          // global quadrant id: p = principal axis (0: z, 1: y, 2: x = branch order of cinterp), sign bits
+          int p, sp, sa, sb;
+          if (kCluster == 1) {
+            p = ql >> 3;
+            sp = (ql & 4) ? -1 : 1; sa = (ql & 2) ? -1 : 1; sb = (ql & 1) ? -1 : 1;
+          } else {
+            // octant = cluster rank: bit0 -> sign x, bit1 -> sign y, bit2 -> sign z
+            const int sx = (crank & 1) ? -1 : 1, sy = (crank & 2) ? -1 : 1, sz = (crank & 4) ? -1 : 1;
+            p = ql;
+            sp = (p == 0) ? sz : (p == 1 ? sy : sx);
+            sa = (p == 2) ? sy : sx;
+            sb = (p == 0) ? sy : sz;
+          }
           // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z)
           const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
           const int lrA = (p == 2) ? lr1 : lr0, llA = (p == 2) ? ll1 : ll0;
           const int lrB = (p == 0) ? lr1 : lr2, llB = (p == 0) ? ll1 : ll2;
-          const bool col_ok = (c < ncol) && r <= (sp > 0 ? lrP : llP) && a <= (sa > 0 ? lrA : llA);
+          const bool col_ok = (it < nitem) && r <= (sp > 0 ? lrP : llP) && a <= (sa > 0 ? lrA : llA);
           const int bmax = col_ok ? min(r, sb > 0 ? lrB : llB) : -1;
+          const int b0 = seg * seglen;
+          const int b1 = min(b0 + seglen - 1, r);      // last b of this segment (loop runs seglen times for all)
           const int nB = (p == 0) ? n1 : n2;
           const int nA = (p == 2) ? n1 : n0;
           const int nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
@@ -182,7 +223,9 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
           const double dr2A = (p == 2) ? dr2_1 : dr2_0;
           const double dr2B = (p == 0) ? dr2_1 : dr2_2;
           const unsigned base = (unsigned)wrap(srcP + sp * r, nP) * strP + (unsigned)wrap(srcA + sa * a, nA) * strA;
-          int posB = srcB;  // b = 0
+          int posB = srcB + sb * b0;
+          if (posB < 0) posB += nB;
+          else if (posB >= nB) posB -= nB;
           // column-level geometry
           const double ua = (a == r) ? 1.0 : (double)a * inv_r;   // 1-dx of cinterp
           const double ca2 = (double)(r * r + a * a);
@@ -190,24 +233,39 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
           // ownership pieces that do not depend on b (see header comment)
           const bool own_col = (a > 0 || sa > 0) && (r > 0 || sp > 0) && (p != 2 || a < r) && (r > 0 || p == 0);
           const bool loss_col = (sp > 0 ? r == lrP : r == llP) || (sa * a == lrA) || (sa * a == -llA);
-          const double* pl = prev + q * r * r;   // plane r-1 patch of this quadrant, stride r
-          double* pc = cur + q * P1 * P1;        // plane r patch, stride r+1
-          const bool a_in = a <= r - 1;          // column a exists in plane r-1
+          const double* pl = prev + ql * r * r;   // plane r-1 patch of this quadrant, stride r
+          double* pc = cur + ql * P1 * P1;        // plane r patch, stride r+1
+          const bool a_in = a <= r - 1;           // column a exists in plane r-1
+          const int blast = min(bmax, r - 1);     // last b with an upstream value in this column
+          // carried upstream values of row b0-1
           double c_own_bm1 = 0.0, c_left_bm1 = 0.0;
-          for (int b = 0; b <= r; ++b) {
+          if (b0 >= 1 && b0 - 1 <= blast) {
+            if (a_in) c_own_bm1 = pl[(b0 - 1) * r + a];
+            if (a >= 1) c_left_bm1 = pl[(b0 - 1) * r + a - 1];
+          }
+          // software pipeline: the grid value of the next cell is requested one iteration ahead
+          double tau_cell_next = 0.0;
+          if (b0 <= bmax) tau_cell_next = P.tau_cell[base + (unsigned)posB * strideB];
+          for (int k = 0; k < seglen; ++k) {
+            const int b = b0 + k;
+            const bool active = (b <= b1) && (b <= bmax);
             // upstream optical depths (cells outside plane r-1 have weight 0; read as 0)
             double c_own = 0.0;
-            if (a_in && b <= r - 1 && b <= bmax) c_own = pl[b * r + a];
+            if (a_in && b <= blast && b <= b1) c_own = pl[b * r + a];
             double c_left = __shfl_up_sync(0xffffffffu, c_own, 1);
-            if (lane == 0) c_left = (a >= 1 && b <= r - 1 && b <= bmax) ? pl[b * r + a - 1] : 0.0;
+            if (lane == 0) c_left = (a >= 1 && b <= blast && b <= b1) ? pl[b * r + a - 1] : 0.0;
             if (a == 0) c_left = 0.0;
             const double t1 = c_left_bm1, t2 = c_own_bm1, t3 = c_left, t4 = c_own;
             c_left_bm1 = c_left;
             c_own_bm1 = c_own;
-            if (b <= bmax) {
-              const unsigned cell = base + (unsigned)posB * strideB;
-              const double tau_cell = P.tau_cell[cell];
-              double tau_in, pathc, volfac;  // volfac = vol_ph * nHI * sigma / ... see below
+            const unsigned cell = base + (unsigned)posB * strideB;
+            const double tau_cell = tau_cell_next;
+            posB += sb;
+            if (posB < 0) posB += nB;
+            else if (posB >= nB) posB -= nB;
+            if (b + 1 <= b1 && b + 1 <= bmax) tau_cell_next = P.tau_cell[base + (unsigned)posB * strideB];
+            if (active) {
+              double tau_in, pathc, volfac;  // volfac = vol_ph * nHI
               bool stop = false;
               if (r == 0) {  // evolve_point.F90:151-160
                 tau_in = 0.0;
@@ -230,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
                 const double rs = fast_rsqrt(q2);
                 pathc = q2 * rs * inv_r;                                   // sqrt(1+(a^2+b^2)/r^2)
                 const double dist2 = fma(dr2B, (double)(b * b), dist_col);  // evolve_point.F90:170-174
-                // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/(volfac)
+                // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/volfac
                 volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
                 if (P.use_lls) {  // :186-196
                   if (P.type_lls == 3) {
@@ -274,32 +332,41 @@ __global__ void __launch_bounds__(kThreads, 2) raytrace_kernel(RtParams P) {
                 }
               }
             }
-            posB += sb;
-            if (posB < 0) posB += nB;
-            else if (posB >= nB) posB -= nB;
           }
         }
-        __syncthreads();  // plane r complete before plane r+1 reads it
+        __syncthreads();  // plane r complete before plane r+1 reads it (quadrants never cross CTAs)
       }
       r_done = rmax;
-      // photon_loss_src = sum over the CTA (plays photon_loss_src_thread, evolve_source.F90:183-186)
+      // photon_loss_src = sum over the work group (plays photon_loss_src_thread, evolve_source.F90:183-186)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
       if (lane == 0) s_red[tid >> 5] = loss;
       __syncthreads();
-      if (tid == 0) {
+      if (kCluster == 1) {
         double t = 0.0;
-        for (int i = 0; i < kThreads / 32; ++i) t += s_red[i];
-        s_loss = t;
+        for (int i = 0; i < kT / 32; ++i) t += s_red[i];   // same order in every thread
+        photon_loss_src = t;
+      } else {
+        if (tid == 0) {
+          double t = 0.0;
+          for (int i = 0; i < kT / 32; ++i) t += s_red[i];
+          cluster.map_shared_rank(&s_slot[pass_parity][0], 0)[crank] = t;   // DSMEM store into rank 0
+        }
+        cluster.sync();
+        const double* slots = cluster.map_shared_rank(&s_slot[pass_parity][0], 0);
+        double t = 0.0;
+        for (int i = 0; i < kCluster; ++i) t += slots[i];   // fixed order: identical in all 8 CTAs
+        photon_loss_src = t;
+        pass_parity ^= 1;
       }
-      __syncthreads();
-      photon_loss_src = s_loss;
     }
-    if (tid == 0) {
+    if (crank == 0 && tid == 0) {
       P.nbox_out[ns] = nbox;              // sum_nbox=sum_nbox+nbox, :219
       P.loss_out[ns] = photon_loss_src;   // photon_loss(1)=photon_loss(1)+photon_loss_src, :216
     }
+    if (kCluster > 1) cluster.sync();     // every peer has read s_work before rank 0 fetches the next ticket
   }
+  if (kCluster > 1) cluster.sync();  // nobody leaves while a peer may still read rank 0's shared memory
 }
 
 // tau_cell = sigma*dr(1) * max(1-max(xh_av,eps),eps) * ndens  (evolve_point.F90:137-145, doric.f90:141-155)
@@ -323,6 +390,7 @@ __global__ void pair_table_kernel(const double* __restrict__ tab, double2* __res
 }  // namespace
 
 size_t raytrace_scratch_doubles_per_cta(int plane_stride) {
+  // sized for the single-CTA kernel (24 quadrants); a cluster CTA uses 3 of them
   return (size_t)2 * kQuadrants * plane_stride * plane_stride;
 }
 
@@ -330,31 +398,76 @@ static size_t rt_smem_bytes(int plane_doubles) {
   return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * plane_doubles * sizeof(double);
 }
 
-int raytrace_configure(int max_radius, int* smem_plane_doubles, int* ctas_per_sm) {
-  // two CTAs per SM: split the opt-in shared memory between them
-  int dev = 0, max_optin = 0;
+int raytrace_configure(int max_radius, RtLaunchInfo* info) {
+  int dev = 0, max_optin = 0, sm_total = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  int sm_total = 0;
   cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
-  int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
-  const int need = kQuadrants * (max_radius + 1) * (max_radius + 1);
-  if (cap > need) cap = need;
-  cap &= ~1;
-  cudaError_t e = cudaFuncSetAttribute(raytrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)rt_smem_bytes(cap));
-  if (e != cudaSuccess) return (int)e;
-  *smem_plane_doubles = cap;
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raytrace_kernel, kThreads, rt_smem_bytes(cap));
-  *ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+  // ---- single-CTA kernel: two CTAs per SM share the opt-in shared memory ----------------------
+  {
+    const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
+    int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
+    const int need = kQuadrants * (max_radius + 1) * (max_radius + 1);
+    if (cap > need) cap = need;
+    cap &= ~1;
+    cudaError_t e = cudaFuncSetAttribute(raytrace_kernel<kThreadsCta, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)rt_smem_bytes(cap));
+    if (e != cudaSuccess) return (int)e;
+    info->smem_plane_doubles = cap;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raytrace_kernel<kThreadsCta, 1>, kThreadsCta, rt_smem_bytes(cap));
+    info->grid_cta = sms * std::max(1, per_sm);
+  }
+  // ---- cluster kernel: one CTA per SM with all of the opt-in shared memory ----------------------
+  {
+    int cap = (int)(((size_t)max_optin - fixed - 2048) / (2 * sizeof(double)));
+    const int need = (kQuadrants / kClusterSize) * (max_radius + 1) * (max_radius + 1);
+    if (cap > need) cap = need;
+    cap &= ~1;
+    cudaError_t e = cudaFuncSetAttribute(raytrace_kernel<kThreadsCl, kClusterSize>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes(cap));
+    if (e != cudaSuccess) return (int)e;
+    info->smem_plane_doubles_cl = cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kClusterSize * sms, 1, 1);
+    cfg.blockDim = dim3(kThreadsCl, 1, 1);
+    cfg.dynamicSmemBytes = rt_smem_bytes(cap);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, raytrace_kernel<kThreadsCl, kClusterSize>, &cfg);
+    if (e != cudaSuccess) return (int)e;
+    info->clusters = std::max(1, nclusters);
+  }
+  info->grid_max = std::max(info->grid_cta, info->clusters * kClusterSize);
   return 0;
 }
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  raytrace_kernel<<<grid, kThreads, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+  raytrace_kernel<kThreadsCta, 1><<<grid, kThreadsCta, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+}
+
+int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kClusterSize * nclusters, 1, 1);
+  cfg.blockDim = dim3(kThreadsCl, 1, 1);
+  cfg.dynamicSmemBytes = rt_smem_bytes(p.smem_plane_doubles_cl);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClusterSize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, raytrace_kernel<kThreadsCl, kClusterSize>, p);
 }
 
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,

@@ -20,6 +20,22 @@ X_ATOL = 1e-6
 DT = 1e6 * 3.15576e7
 
 
+@pytest.fixture(params=["auto", "cta", "cluster"], autouse=True)
+def routing(request, monkeypatch):
+    """every test runs with the default routing of sources to the two ray-trace kernels, with the
+    one-CTA-per-source kernel only, and with the cluster-of-8 kernel only"""
+    if request.param == "cta":
+        monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
+        monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
+    elif request.param == "cluster":
+        monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "0")
+        monkeypatch.setenv("C2B_DEBUG_CLUSTER", "1")
+    else:
+        monkeypatch.delenv("C2B_CLUSTER_MIN_NBOX", raising=False)
+        monkeypatch.delenv("C2B_DEBUG_CLUSTER", raising=False)
+    return request.param
+
+
 def _rates_close(gpu, cpu, rtol=RATE_RTOL):
     """relative tolerance on every cell that has a rate; cells the oracle leaves at exactly 0 must be 0"""
     gpu = np.asarray(gpu).reshape(-1)
