@@ -55,6 +55,7 @@ struct RtLaunchInfo {
   int smem_plane_doubles, smem_plane_doubles_cl;
   int grid_cta;    // resident CTAs of the single-CTA kernel
   int clusters;    // resident clusters of the cluster kernel
+  int cluster_size;
   int grid_max;    // CTAs the scratch must be sized for
 };
 // sets the kernels' shared-memory attributes and queries the resident grid sizes

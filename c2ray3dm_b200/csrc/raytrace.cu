@@ -43,30 +43,40 @@ namespace c2b {
 namespace {
 
 constexpr int kThreadsCta = 256;   // one CTA per source
-constexpr int kThreadsCl = 512;    // cluster of 8 CTAs per source
-constexpr int kClusterSize = 8;
 constexpr int kQuadrants = 24;
 
+// max/min of two NON-NEGATIVE doubles through their bit patterns (integer order == numeric order there);
+// avoids the NaN-propagating DSETP.MAX/FSEL/LOP3 sequence fmax() and ?: compile to.
+__device__ __forceinline__ double pos_max(double x, double y) {
+  return __longlong_as_double(max(__double_as_longlong(x), __double_as_longlong(y)));
+}
+__device__ __forceinline__ double pos_min(double x, double y) {
+  return __longlong_as_double(min(__double_as_longlong(x), __double_as_longlong(y)));
+}
+
+// 1/x: hardware seed (>= 20 bits) refined with y*(1+e+e^2), e = 1-x*y  =>  relative error ~e^3 < 1e-17
 __device__ __forceinline__ double fast_rcp(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(t, y, y);
 }
 
+// 1/sqrt(x): hardware seed refined with y*(1 + e/2 + 3e^2/8), e = 1-x*y*y  =>  relative error ~e^3
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  // two Newton steps: y <- y*(1.5 - 0.5*x*y*y)
-  double h = 0.5 * x;
-  double t = fma(-h * y, y, 0.5);
-  y = fma(y, t, y);
-  t = fma(-h * y, y, 0.5);
-  y = fma(y, t, y);
-  return y;
+  const double e = fma(-(x * y), y, 1.0);
+  const double t = fma(0.375, e, 0.5) * e;
+  return fma(y, t, y);
+}
+
+// x > y ? x : y on the FP64 compare without fmax()'s NaN handling (3 instructions)
+__device__ __forceinline__ double sel_max(double x, double y) {
+  double r;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\t}" : "=d"(r) : "d"(x), "d"(y));
+  return r;
 }
 
 // table coordinate odpos = 1 + (log10(max(1e-20,tau)) - minlogtau)/dlogtau of
@@ -74,7 +84,7 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 // logtab[j] = {1/c_j, A + B*log2(c_j)}, c_j = 1 + (j+0.5)/128; coef = B/ln2 * {1,-1/2,1/3,-1/4,1/5}
 __device__ __forceinline__ double table_coord(double tau, const double2* __restrict__ logtab,
                                               const RtParams& P) {
-  const double t = fmax(tau, 1.0e-20);
+  const double t = sel_max(tau, 1.0e-20);
   const int hi = __double2hiint(t);
   const int lo = __double2loint(t);
   const int e = (hi >> 20) - 1023;
@@ -88,7 +98,7 @@ __device__ __forceinline__ double table_coord(double tau, const double2* __restr
   q = fma(rr, q, P.logc[0]);
   double od = fma(P.logB, (double)e, lt.y);
   od = fma(rr, q, od);
-  return fmin(od, (double)kNumTau);
+  return pos_min(od, (double)kNumTau);  // od >= 0 because tau >= 1e-20
 }
 
 // read_table (radiation_photoionrates.F90:212-228) on the (value, forward difference) pairs
@@ -97,6 +107,28 @@ __device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, do
   const double res = od - (double)ipos;
   const double2 t = tab[ipos];
   return fma(t.y, res, t.x);
+}
+
+// photoion_rates / photo_lookuptable (radiation_photoionrates.F90:71-317) for one stellar source:
+// Gamma_cell*vol_ph = F*(thick(tau_in)-thick(tau_out)), or F*dtau*thin(tau_in) below tau_photo_limit.
+__device__ __forceinline__ void photo_rates(double tau_in, double tau_out, double normflux,
+                                            const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
+                                            const RtParams& P, double& phi_all, double& phi_out) {
+  const double od_in = table_coord(tau_in, s_logtab, P);
+  const double phi_in = normflux * lerp_pairs(s_thick, od_in);
+  const double dtau = tau_out - tau_in;
+  if (fabs(dtau) > P.tau_photo_limit) {
+    const double od_out = table_coord(tau_out, s_logtab, P);
+    phi_out = normflux * lerp_pairs(s_thick, od_out);
+    phi_all = phi_in - phi_out;
+  } else {
+    const int ipos = (int)od_in;
+    const double res = od_in - (double)ipos;
+    const double lo = P.thin[ipos];
+    const double thin = lo + (P.thin[min(kNumTau, ipos + 1)] - lo) * res;
+    phi_all = normflux * dtau * thin;
+    phi_out = phi_in - phi_all;
+  }
 }
 
 __device__ __forceinline__ int wrap(int x, int n) {
@@ -108,9 +140,16 @@ __device__ __forceinline__ int wrap(int x, int n) {
 
 // One CTA (kCluster == 1) or one cluster of 8 CTAs (kCluster == 8, one CTA per octant with its three
 // face quadrants) per source.
-template <int kT, int kCluster>
+// kLls: 0 = no LLS, 1 = homogeneous, 2 = LLS_grid, 3 = R_max barrier (LLS.F90:107-116); kDebug adds
+// the coldensh_out diagnostic store.
+// kGroups: the CTA's warps form kGroups independent groups, each owning kNq/kGroups quadrants and its own
+// named barrier, so a group waiting for its shell to complete does not idle the others.
+template <int kT, int kCluster, int kGroups, int kLls, bool kDebug>
 __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(RtParams P) {
   constexpr int kNq = kQuadrants / kCluster;        // face quadrants handled by this CTA
+  constexpr int kNqg = kNq / kGroups;               // ... by one warp group
+  constexpr int kTg = kT / kGroups;                 // threads per group
+  static_assert(kNq % kGroups == 0 && kT % kGroups == 0 && kTg % 32 == 0, "bad group split");
   extern __shared__ double2 smem2[];
   double2* s_thick = smem2;                         // kTableLen pairs
   double2* s_logtab = smem2 + kTableLen;            // 128 pairs
@@ -121,15 +160,19 @@ __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(R
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int grp = tid / kTg;
+  const int gtid = tid - grp * kTg;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = (kCluster > 1) ? cluster.block_rank() : 0u;
   const unsigned cid = (kCluster > 1) ? (blockIdx.x / kCluster) : blockIdx.x;   // work-group index
   (void)cid;
   for (int i = tid; i < kTableLen; i += kT) s_thick[i] = P.thick2[i];
   for (int i = tid; i < 128; i += kT) s_logtab[i] = P.logtab[i];
-  const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;  // per shared plane buffer
-  const size_t gplane = (size_t)kNq * P.plane_stride * P.plane_stride;
-  double* gbuf0 = P.scratch + (size_t)blockIdx.x * 2 * gplane;
+  // per group: two shared plane buffers of `cap` doubles and two global ones of kNqg*S*S
+  const int cap = (((kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl) / kGroups) & ~1;
+  double* s_planes_g = s_planes + (size_t)grp * 2 * cap;
+  const size_t gplane = (size_t)kNqg * P.plane_stride * P.plane_stride;
+  double* gbuf0 = P.scratch + ((size_t)blockIdx.x * kGroups + grp) * 2 * gplane;
   double* gbuf1 = gbuf0 + gplane;
   const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
   const unsigned st0 = 1u, st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;
@@ -170,38 +213,59 @@ __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(R
       lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
       const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
       double loss = 0.0;
+      if (r_done < 0) {
+        // shell 0 = the source cell (evolve_point.F90:151-160): coldensh_in=0, path=dr/2, vol_ph=cell volume.
+        // Every quadrant of the group stores it as its plane 0; the (+,+,+) z quadrant owns it.
+        if (gtid < kNqg) {
+          const int qc = grp * kNqg + gtid;
+          const int oct = (int)crank * (8 / kCluster) + qc / 3;
+          const unsigned cell = (unsigned)src2 * st2 + (unsigned)src1 * st1 + (unsigned)src0;
+          const double tau_cell = P.tau_cell[cell];
+          const double tau_out = 0.5 * tau_cell;
+          s_planes_g[gtid] = tau_out;   // plane 0 always fits in shared memory
+          if (oct == 0 && qc - (qc / 3) * 3 == 0) {
+            if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
+            if (normflux > 0.0) {
+              double phi_all, phi_out;
+              photo_rates(0.0, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
+              // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
+              const double photo_cell = phi_all * fast_rcp(vol_cell * tau_cell * P.inv_sigma_dr0);
+              if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);
+            }
+          }
+        }
+        if (kGroups == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kTg) : "memory");
+        r_done = 0;
+      }
       for (int r = r_done + 1; r <= rmax; ++r) {
         const int P1 = r + 1;
         // plane buffers of shell r (cur) and r-1 (prev): shared while they fit, else global scratch
-        double* cur = (kNq * P1 * P1 <= cap) ? (s_planes + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
-        const double* prev = (kNq * r * r <= cap) ? (s_planes + ((r - 1) & 1) * cap)
-                                                  : (((r - 1) & 1) ? gbuf1 : gbuf0);
-        const double inv_r = (r > 0) ? 1.0 / (double)r : 0.0;
+        double* cur = (kNqg * P1 * P1 <= cap) ? (s_planes_g + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
+        const double* prev = (kNqg * r * r <= cap) ? (s_planes_g + ((r - 1) & 1) * cap)
+                                                   : (((r - 1) & 1) ? gbuf1 : gbuf0);
+        const double inv_r = 1.0 / (double)r;
         // work items: (segment of b, quadrant, column a), a fastest so that a warp spans adjacent columns
-        const int ncol = kNq * P1;
-        int nseg = kT / ncol;
+        const int ncol = kNqg * P1;
+        int nseg = kTg / ncol;
         nseg = max(1, min(nseg, P1 / 2));
         const int seglen = (P1 + nseg - 1) / nseg;
         const int nitem = ncol * nseg;
-        for (int it0 = tid - lane; it0 < nitem; it0 += kT) {  // warp-uniform trip count
+        for (int it0 = gtid - lane; it0 < nitem; it0 += kTg) {  // warp-uniform trip count
           const int it = it0 + lane;
           const int seg = it / ncol;
           const int c = it - seg * ncol;
           const int ql = c / P1;
           const int a = c - ql * P1;
-          // global quadrant id: p = principal axis (0: z, 1: y, 2: x = branch order of cinterp), sign bits
-          int p, sp, sa, sb;
-          if (kCluster == 1) {
-            p = ql >> 3;
-            sp = (ql & 4) ? -1 : 1; sa = (ql & 2) ? -1 : 1; sb = (ql & 1) ? -1 : 1;
-          } else {
-            // octant = cluster rank: bit0 -> sign x, bit1 -> sign y, bit2 -> sign z
-            const int sx = (crank & 1) ? -1 : 1, sy = (crank & 2) ? -1 : 1, sz = (crank & 4) ? -1 : 1;
-            p = ql;
-            sp = (p == 0) ? sz : (p == 1 ? sy : sx);
-            sa = (p == 2) ? sy : sx;
-            sb = (p == 0) ? sy : sz;
-          }
+          // quadrant: the CTA (cluster rank) owns 8/kCluster octants, an octant has one quadrant per
+          // principal axis p (0: z, 1: y, 2: x = branch order of cinterp); octant bit0/1/2 = sign of x/y/z
+          const int qc = grp * kNqg + ql;
+          const int oct = (int)crank * (8 / kCluster) + qc / 3;
+          const int p = qc - (qc / 3) * 3;
+          const int sx = (oct & 1) ? -1 : 1, sy = (oct & 2) ? -1 : 1, sz = (oct & 4) ? -1 : 1;
+          const int sp = (p == 0) ? sz : (p == 1 ? sy : sx);
+          const int sa = (p == 2) ? sy : sx;
+          const int sb = (p == 0) ? sy : sz;
           // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z)
           const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
           const int lrA = (p == 2) ? lr1 : lr0, llA = (p == 2) ? ll1 : ll0;
@@ -227,102 +291,98 @@ __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(R
           if (posB < 0) posB += nB;
           else if (posB >= nB) posB -= nB;
           // column-level geometry
-          const double ua = (a == r) ? 1.0 : (double)a * inv_r;   // 1-dx of cinterp
+          const double ua = (double)a * inv_r;   // 1-dx of cinterp (a==r gives 1 to an ulp; the cells it would exclude read as 0)
           const double ca2 = (double)(r * r + a * a);
           const double dist_col = dr2P * (double)(r * r) + dr2A * (double)(a * a);
           // ownership pieces that do not depend on b (see header comment)
-          const bool own_col = (a > 0 || sa > 0) && (r > 0 || sp > 0) && (p != 2 || a < r) && (r > 0 || p == 0);
+          const bool own_col = (a > 0 || sa > 0) && (p != 2 || a < r);
           const bool loss_col = (sp > 0 ? r == lrP : r == llP) || (sa * a == lrA) || (sa * a == -llA);
-          const double* pl = prev + ql * r * r;   // plane r-1 patch of this quadrant, stride r
-          double* pc = cur + ql * P1 * P1;        // plane r patch, stride r+1
           const bool a_in = a <= r - 1;           // column a exists in plane r-1
           const int blast = min(bmax, r - 1);     // last b with an upstream value in this column
+          const int nact = max(0, min(b1, bmax) - b0 + 1);   // cells of this segment that exist
+          const int nup = max(0, min(b1, blast) - b0 + 1);   // ... that have an upstream cell (a|a-1, b)
+          const double* pown = prev + ql * r * r + b0 * r + a;   // plane r-1 patch (stride r), row b0
+          double* pout = cur + ql * P1 * P1 + b0 * P1 + a;       // plane r patch (stride r+1)
           // carried upstream values of row b0-1
           double c_own_bm1 = 0.0, c_left_bm1 = 0.0;
           if (b0 >= 1 && b0 - 1 <= blast) {
-            if (a_in) c_own_bm1 = pl[(b0 - 1) * r + a];
-            if (a >= 1) c_left_bm1 = pl[(b0 - 1) * r + a - 1];
+            if (a_in) c_own_bm1 = pown[-r];
+            if (a >= 1) c_left_bm1 = pown[-r - 1];
           }
-          // software pipeline: the grid value of the next cell is requested one iteration ahead
-          double tau_cell_next = 0.0;
-          if (b0 <= bmax) tau_cell_next = P.tau_cell[base + (unsigned)posB * strideB];
+          // software pipeline: the plane and grid values of the next cell are requested one iteration ahead
+          unsigned cell_next = base + (unsigned)posB * strideB;
+          double tau_cell_next = 0.0, c_own_next = 0.0, c_lane0_next = 0.0;
+          if (nact > 0) tau_cell_next = P.tau_cell[cell_next];
+          if (a_in && nup > 0) c_own_next = pown[0];
+          if (lane == 0 && a >= 1 && nup > 0) c_lane0_next = pown[-1];
+          double bd = (double)b0;
+          const int dcell = sb * (int)strideB, dwrap = (int)strideB * nB;
           for (int k = 0; k < seglen; ++k) {
             const int b = b0 + k;
-            const bool active = (b <= b1) && (b <= bmax);
+            const bool active = k < nact;
             // upstream optical depths (cells outside plane r-1 have weight 0; read as 0)
-            double c_own = 0.0;
-            if (a_in && b <= blast && b <= b1) c_own = pl[b * r + a];
+            const double c_own = c_own_next;
             double c_left = __shfl_up_sync(0xffffffffu, c_own, 1);
-            if (lane == 0) c_left = (a >= 1 && b <= blast && b <= b1) ? pl[b * r + a - 1] : 0.0;
+            if (lane == 0) c_left = c_lane0_next;
             if (a == 0) c_left = 0.0;
             const double t1 = c_left_bm1, t2 = c_own_bm1, t3 = c_left, t4 = c_own;
             c_left_bm1 = c_left;
             c_own_bm1 = c_own;
-            const unsigned cell = base + (unsigned)posB * strideB;
+            const unsigned cell = cell_next;
             const double tau_cell = tau_cell_next;
+            // advance to row b+1 and request its inputs
+            pown += r;
             posB += sb;
-            if (posB < 0) posB += nB;
-            else if (posB >= nB) posB -= nB;
-            if (b + 1 <= b1 && b + 1 <= bmax) tau_cell_next = P.tau_cell[base + (unsigned)posB * strideB];
+            int cn = (int)cell + dcell;
+            if (posB < 0) { posB += nB; cn += dwrap; }
+            else if (posB >= nB) { posB -= nB; cn -= dwrap; }
+            cell_next = (unsigned)cn;
+            c_own_next = 0.0;
+            if (k + 1 < nact) tau_cell_next = P.tau_cell[cell_next];
+            if (k + 1 < nup) {
+              if (a_in) c_own_next = pown[0];
+              if (lane == 0 && a >= 1) c_lane0_next = pown[-1];
+            } else {
+              c_lane0_next = 0.0;
+            }
             if (active) {
-              double tau_in, pathc, volfac;  // volfac = vol_ph * nHI
               bool stop = false;
-              if (r == 0) {  // evolve_point.F90:151-160
-                tau_in = 0.0;
-                pathc = 0.5;
-                // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
-                volfac = vol_cell * tau_cell * P.inv_sigma_dr0;
-              } else {
-                // cinterp, column_density.f90:108-171, with a common denominator
-                const double ub = (b == r) ? 1.0 : (double)b * inv_r;  // 1-dy
-                const double va = 1.0 - ua, vb = 1.0 - ub;
-                const double s1 = ua * ub, s2 = ub * va, s3 = ua * vb, s4 = va * vb;
-                const double m1 = fmax(0.6, t1), m2 = fmax(0.6, t2), m3 = fmax(0.6, t3), m4 = fmax(0.6, t4);
-                const double p12 = m1 * m2, p34 = m3 * m4;
-                const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
-                const double num = fma(t1, e1, fma(t2, e2, fma(t3, e3, t4 * e4)));
-                const double den = (e1 + e2) + (e3 + e4);
-                tau_in = num * fast_rcp(den);
-                if (r == 1 && (a == 1 || b == 1)) tau_in *= (a == 1 && b == 1) ? P.sqrt3 : P.sqrt2;  // :152-158
-                const double q2 = ca2 + (double)(b * b);
-                const double rs = fast_rsqrt(q2);
-                pathc = q2 * rs * inv_r;                                   // sqrt(1+(a^2+b^2)/r^2)
-                const double dist2 = fma(dr2B, (double)(b * b), dist_col);  // evolve_point.F90:170-174
-                // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/volfac
-                volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
-                if (P.use_lls) {  // :186-196
-                  if (P.type_lls == 3) {
-                    if (dist2 > P.rmax_lls2) stop = true;
-                  } else {
-                    const double tl = (P.type_lls == 2) ? (double)P.lls_grid[cell] * P.sigma_HI : P.tau_lls;
-                    tau_in = fma(tl, pathc, tau_in);
-                  }
-                }
+              // cinterp, column_density.f90:108-171, with a common denominator
+              const double ub = bd * inv_r;  // 1-dy
+              const double va = 1.0 - ua, vb = 1.0 - ub;
+              const double s1 = ua * ub, s2 = ub * va, s3 = ua * vb, s4 = va * vb;
+              // weightf = 1/max(0.6, tau), column_density.f90:276-293
+              const double m1 = sel_max(t1, 0.6), m2 = sel_max(t2, 0.6);
+              const double m3 = sel_max(t3, 0.6), m4 = sel_max(t4, 0.6);
+              const double p12 = m1 * m2, p34 = m3 * m4;
+              const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
+              const double num = fma(t1, e1, fma(t2, e2, fma(t3, e3, t4 * e4)));
+              const double den = (e1 + e2) + (e3 + e4);
+              double tau_in = num * fast_rcp(den);
+              if (r == 1 && (a == 1 || b == 1)) tau_in *= (a == 1 && b == 1) ? P.sqrt3 : P.sqrt2;  // :152-158
+              const double b2 = bd * bd;
+              const double q2 = ca2 + b2;
+              const double rs = fast_rsqrt(q2);
+              const double pathc = q2 * rs * inv_r;                        // sqrt(1+(a^2+b^2)/r^2)
+              const double dist2 = fma(dr2B, b2, dist_col);                // evolve_point.F90:170-174
+              // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/volfac
+              const double volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
+              if (kLls == 3) {  // evolve_point.F90:186-196
+                if (dist2 > P.rmax_lls2) stop = true;
+              } else if (kLls == 2) {
+                tau_in = fma((double)P.lls_grid[cell] * P.sigma_HI, pathc, tau_in);
+              } else if (kLls == 1) {
+                tau_in = fma(P.tau_lls, pathc, tau_in);
               }
               if (tau_in > tau_stop) stop = true;                          // :201
               const double tau_out = fma(tau_cell, pathc, tau_in);         // :247-248
-              pc[b * P1 + a] = tau_out;
+              *pout = tau_out;
               const bool owner = own_col && (b > 0 || sb > 0) && (p == 0 || b < r);
               if (owner) {
-                if (P.coldens_dbg) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
+                if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
                 if (!stop && normflux > 0.0) {
-                  // photoion_rates / photo_lookuptable, radiation_photoionrates.F90:71-317
-                  const double od_in = table_coord(tau_in, s_logtab, P);
-                  const double phi_in = normflux * lerp_pairs(s_thick, od_in);
-                  double phi_out, phi_all;
-                  const double dtau = tau_out - tau_in;
-                  if (fabs(dtau) > P.tau_photo_limit) {
-                    const double od_out = table_coord(tau_out, s_logtab, P);
-                    phi_out = normflux * lerp_pairs(s_thick, od_out);
-                    phi_all = phi_in - phi_out;
-                  } else {
-                    const int ipos = (int)od_in;
-                    const double res = od_in - (double)ipos;
-                    const double lo = P.thin[ipos];
-                    const double thin = lo + (P.thin[min(kNumTau, ipos + 1)] - lo) * res;
-                    phi_all = normflux * dtau * thin;
-                    phi_out = phi_in - phi_all;
-                  }
+                  double phi_all, phi_out;
+                  photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
                   const double inv_vol = fast_rcp(volfac);
                   const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
                   if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);  // :283-284
@@ -332,9 +392,13 @@ __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(R
                 }
               }
             }
+            pout += P1;
+            bd += 1.0;
           }
         }
-        __syncthreads();  // plane r complete before plane r+1 reads it (quadrants never cross CTAs)
+        // plane r complete before plane r+1 reads it (quadrants never cross groups)
+        if (kGroups == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kTg) : "memory");
       }
       r_done = rmax;
       // photon_loss_src = sum over the work group (plays photon_loss_src_thread, evolve_source.F90:183-186)
@@ -398,76 +462,115 @@ static size_t rt_smem_bytes(int plane_doubles) {
   return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * plane_doubles * sizeof(double);
 }
 
+typedef void (*RtKernel)(RtParams);
+
+template <int kT, int kCluster, int kGroups>
+static RtKernel pick_kernel(int lls, bool debug) {
+  if (debug) {
+    switch (lls) {
+      case 0: return raytrace_kernel<kT, kCluster, kGroups, 0, true>;
+      case 1: return raytrace_kernel<kT, kCluster, kGroups, 1, true>;
+      case 2: return raytrace_kernel<kT, kCluster, kGroups, 2, true>;
+      default: return raytrace_kernel<kT, kCluster, kGroups, 3, true>;
+    }
+  }
+  switch (lls) {
+    case 0: return raytrace_kernel<kT, kCluster, kGroups, 0, false>;
+    case 1: return raytrace_kernel<kT, kCluster, kGroups, 1, false>;
+    case 2: return raytrace_kernel<kT, kCluster, kGroups, 2, false>;
+    default: return raytrace_kernel<kT, kCluster, kGroups, 3, false>;
+  }
+}
+
+// work-group shapes of the many-CTA kernel (C2B_CLUSTER_VARIANT selects one)
+struct ClusterVariant {
+  int threads, cluster, groups;
+  RtKernel (*pick)(int, bool);
+};
+static const ClusterVariant kVariants[] = {
+    {512, 8, 1, pick_kernel<512, 8, 1>},  // 0: one octant per CTA, one barrier domain
+    {480, 8, 3, pick_kernel<480, 8, 3>},  // 1: one octant per CTA, one warp group per face quadrant
+    {512, 4, 2, pick_kernel<512, 4, 2>},  // 2: two octants per CTA, one group per octant
+    {512, 4, 1, pick_kernel<512, 4, 1>},  // 3
+    {512, 2, 2, pick_kernel<512, 2, 2>},  // 4: four octants per CTA, two groups
+    {576, 4, 6, pick_kernel<576, 4, 6>},  // 5: two octants per CTA, one group per face quadrant
+};
+static int g_variant = 1;
+
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, const ClusterVariant& v, int nclusters,
+                           size_t smem, cudaStream_t stream) {
+  *cfg = cudaLaunchConfig_t{};
+  cfg->gridDim = dim3(v.cluster * nclusters, 1, 1);
+  cfg->blockDim = dim3(v.threads, 1, 1);
+  cfg->dynamicSmemBytes = smem;
+  cfg->stream = stream;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = v.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+
 int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   int dev = 0, max_optin = 0, sm_total = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* env = getenv("C2B_CLUSTER_VARIANT")) {
+    const int v = atoi(env);
+    if (v >= 0 && v < (int)(sizeof(kVariants) / sizeof(kVariants[0]))) g_variant = v;
+  }
+  const ClusterVariant& V = kVariants[g_variant];
   const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
   // ---- single-CTA kernel: two CTAs per SM share the opt-in shared memory ----------------------
-  {
-    const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
-    int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
-    const int need = kQuadrants * (max_radius + 1) * (max_radius + 1);
-    if (cap > need) cap = need;
-    cap &= ~1;
-    cudaError_t e = cudaFuncSetAttribute(raytrace_kernel<kThreadsCta, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)rt_smem_bytes(cap));
-    if (e != cudaSuccess) return (int)e;
-    info->smem_plane_doubles = cap;
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raytrace_kernel<kThreadsCta, 1>, kThreadsCta, rt_smem_bytes(cap));
-    info->grid_cta = sms * std::max(1, per_sm);
-  }
+  const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
+  int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
+  cap = std::min(cap, kQuadrants * (max_radius + 1) * (max_radius + 1)) & ~1;
   // ---- cluster kernel: one CTA per SM with all of the opt-in shared memory ----------------------
-  {
-    int cap = (int)(((size_t)max_optin - fixed - 2048) / (2 * sizeof(double)));
-    const int need = (kQuadrants / kClusterSize) * (max_radius + 1) * (max_radius + 1);
-    if (cap > need) cap = need;
-    cap &= ~1;
-    cudaError_t e = cudaFuncSetAttribute(raytrace_kernel<kThreadsCl, kClusterSize>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes(cap));
-    if (e != cudaSuccess) return (int)e;
-    info->smem_plane_doubles_cl = cap;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kClusterSize * sms, 1, 1);
-    cfg.blockDim = dim3(kThreadsCl, 1, 1);
-    cfg.dynamicSmemBytes = rt_smem_bytes(cap);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kClusterSize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int nclusters = 0;
-    e = cudaOccupancyMaxActiveClusters(&nclusters, raytrace_kernel<kThreadsCl, kClusterSize>, &cfg);
-    if (e != cudaSuccess) return (int)e;
-    info->clusters = std::max(1, nclusters);
-  }
-  info->grid_max = std::max(info->grid_cta, info->clusters * kClusterSize);
+  int cap_cl = (int)(((size_t)max_optin - fixed - 2048) / (2 * sizeof(double)));
+  cap_cl = std::min(cap_cl, (kQuadrants / V.cluster) * (max_radius + 1) * (max_radius + 1) + 2 * V.groups) & ~1;
+  for (int dbg = 0; dbg < 2; ++dbg)
+    for (int lls = 0; lls < 4; ++lls) {
+      cudaError_t e = cudaFuncSetAttribute(pick_kernel<kThreadsCta, 1, 1>(lls, dbg != 0),
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes(cap));
+      if (e != cudaSuccess) return (int)e;
+      e = cudaFuncSetAttribute(V.pick(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)rt_smem_bytes(cap_cl));
+      if (e != cudaSuccess) return (int)e;
+    }
+  info->smem_plane_doubles = cap;
+  info->smem_plane_doubles_cl = cap_cl;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<kThreadsCta, 1, 1>(1, false), kThreadsCta,
+                                                rt_smem_bytes(cap));
+  info->grid_cta = sms * std::max(1, per_sm);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  cluster_config(&cfg, attr, V, sms, rt_smem_bytes(cap_cl), nullptr);
+  int nclusters = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, V.pick(1, false), &cfg);
+  if (e != cudaSuccess) return (int)e;
+  info->clusters = std::max(1, nclusters);
+  info->cluster_size = V.cluster;
+  info->grid_max = info->grid_cta + info->clusters * V.cluster;   // both kernels may run concurrently
   return 0;
 }
 
+static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
+
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  raytrace_kernel<kThreadsCta, 1><<<grid, kThreadsCta, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+  pick_kernel<kThreadsCta, 1, 1>(lls_mode(p), p.coldens_dbg != nullptr)
+      <<<grid, kThreadsCta, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
 }
 
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(kClusterSize * nclusters, 1, 1);
-  cfg.blockDim = dim3(kThreadsCl, 1, 1);
-  cfg.dynamicSmemBytes = rt_smem_bytes(p.smem_plane_doubles_cl);
-  cfg.stream = stream;
+  const ClusterVariant& V = kVariants[g_variant];
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kClusterSize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, raytrace_kernel<kThreadsCl, kClusterSize>, p);
+  cluster_config(&cfg, attr, V, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl), stream);
+  return (int)cudaLaunchKernelEx(&cfg, V.pick(lls_mode(p), p.coldens_dbg != nullptr), p);
 }
 
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
