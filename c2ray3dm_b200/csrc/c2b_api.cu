@@ -70,8 +70,10 @@ struct c2b_handle {
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
   RtLaunchInfo rt;             // shared-memory plane capacities and resident grid sizes
   int* d_work2 = nullptr;      // work list of the cluster kernel
+  int *d_nseg_cta = nullptr, *d_nseg_cl = nullptr;
   std::vector<int> nbox_pred;  // per source: nbox of the previous trace (routing + longest-first order)
-  int cluster_min_nbox = 3;    // sources predicted to need >= this many subboxes go to the cluster kernel
+  int cluster_min_nbox = 3;    // sources predicted to need >= this many subboxes may go to the cluster kernel
+  int cluster_max_sources = 0; // ... but only while there are too few of them to fill the GPU one CTA each
   bool have_tables = false, have_density = false, have_xh = false, have_geometry = false;
   // sources
   int NumSrc = 0, nwork = 0;
@@ -285,7 +287,17 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   h->plane_stride = smax + 1;
   if (raytrace_configure(smax, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
   h->rt_grid = h->rt.grid_max;
+  h->cluster_max_sources = 4 * h->rt.clusters;
   if (const char* env = getenv("C2B_CLUSTER_MIN_NBOX")) h->cluster_min_nbox = atoi(env);
+  if (const char* env = getenv("C2B_CLUSTER_MAX_SOURCES")) h->cluster_max_sources = atoi(env);
+  {
+    std::vector<int> t_cta, t_cl;
+    raytrace_nseg_tables(smax, t_cta, t_cl);
+    if ((e = cudaMalloc(&h->d_nseg_cta, t_cta.size() * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_nseg_cl, t_cl.size() * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemcpy(h->d_nseg_cta, t_cta.data(), t_cta.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_nseg_cl, t_cl.data(), t_cl.size() * sizeof(int), cudaMemcpyHostToDevice);
+  }
   const size_t scratch = raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt_grid;
   if ((e = cudaMalloc(&h->d_scratch, scratch * sizeof(double))) != cudaSuccess) return bail("cudaMalloc scratch", e);
   h->chem_blocks = chemistry_blocks();
@@ -307,7 +319,7 @@ void c2b_destroy(c2b_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
-  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
+  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
   cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
@@ -623,6 +635,8 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.srcpos = h->d_srcpos;
   rp.normflux = h->d_normflux;
   rp.work = d_work;
+  rp.nseg_cta = h->d_nseg_cta;
+  rp.nseg_cl = h->d_nseg_cl;
   rp.nwork = nwork;
   rp.ticket = h->d_ticket;
   rp.scratch = h->d_scratch;
@@ -732,8 +746,21 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     CU(h, cudaMemsetAsync(h->d_loss, 0, (size_t)h->NumSrc * sizeof(double), h->stream));
     // route by the subbox count of the previous trace, longest first (the work queue is dynamic, so
     // the order only affects load balance and the order of the atomic additions)
+    // A long trace parallelises over a cluster of 8 CTAs (one per octant); with many sources one CTA per
+    // source already fills the GPU and has less synchronisation, so the cluster kernel is used only
+    // while the long traces are few.  Sources never traced before (prediction 0) count as long when the
+    // whole list is short.
     std::vector<int> small, large;
-    for (int w : h->work) (h->nbox_pred[w] >= h->cluster_min_nbox ? large : small).push_back(w);
+    const bool few = (int)h->work.size() <= h->cluster_max_sources;
+    for (int w : h->work) {
+      const int pred = h->nbox_pred[w];
+      const bool is_large = pred >= h->cluster_min_nbox || (pred == 0 && few && h->cluster_min_nbox < 100000);
+      (is_large ? large : small).push_back(w);
+    }
+    if ((int)large.size() > h->cluster_max_sources) {
+      small.insert(small.end(), large.begin(), large.end());
+      large.clear();
+    }
     std::stable_sort(large.begin(), large.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
     std::stable_sort(small.begin(), small.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
     if (!small.empty())

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "../../include/c2ray_b200.h"
 
 namespace c2b {
@@ -33,6 +35,8 @@ struct RtParams {
   const int* srcpos;        // 3 x NumSrc, 1-based (sourceprops.F90:56)
   const double* normflux;   // NormFlux_stellar(1:NumSrc)
   const int* work;          // source indices (0-based) this rank traces, in order
+  const int* nseg_cta;      // per shell radius: b-segments per column (single-CTA kernel / cluster kernel)
+  const int* nseg_cl;
   int nwork;
   unsigned int* ticket;     // dynamic work counter (plays do_grid_master, master_slave.F90:124-231)
   double* scratch;          // per-CTA global plane storage: [grid][2][24][S][S]
@@ -61,6 +65,7 @@ struct RtLaunchInfo {
 // sets the kernels' shared-memory attributes and queries the resident grid sizes
 int raytrace_configure(int max_radius, RtLaunchInfo* info);
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream);
+void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl);
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
                     double eps, cudaStream_t stream);
 void launch_pair_table(const double* tab, double2* out, cudaStream_t stream);

@@ -35,6 +35,9 @@
 // the rates at 1e-6 relative as BASELINE.json requires).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "c2b_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -145,7 +148,7 @@ __device__ __forceinline__ int wrap(int x, int n) {
 // kGroups: the CTA's warps form kGroups independent groups, each owning kNq/kGroups quadrants and its own
 // named barrier, so a group waiting for its shell to complete does not idle the others.
 template <int kT, int kCluster, int kGroups, int kLls, bool kDebug>
-__global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(RtParams P) {
+__global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtParams P) {
   constexpr int kNq = kQuadrants / kCluster;        // face quadrants handled by this CTA
   constexpr int kNqg = kNq / kGroups;               // ... by one warp group
   constexpr int kTg = kT / kGroups;                 // threads per group
@@ -247,8 +250,7 @@ __global__ void __launch_bounds__(kT, (kCluster == 1) ? 2 : 1) raytrace_kernel(R
         const double inv_r = 1.0 / (double)r;
         // work items: (segment of b, quadrant, column a), a fastest so that a warp spans adjacent columns
         const int ncol = kNqg * P1;
-        int nseg = kTg / ncol;
-        nseg = max(1, min(nseg, P1 / 2));
+        const int nseg = (kCluster == 1) ? P.nseg_cta[r] : P.nseg_cl[r];   // host-tuned split of the columns along b
         const int seglen = (P1 + nseg - 1) / nseg;
         const int nitem = ncol * nseg;
         for (int it0 = gtid - lane; it0 < nitem; it0 += kTg) {  // warp-uniform trip count
@@ -486,6 +488,7 @@ static RtKernel pick_kernel(int lls, bool debug) {
 struct ClusterVariant {
   int threads, cluster, groups;
   RtKernel (*pick)(int, bool);
+  int ctas_per_sm() const { return threads <= 256 ? 2 : 1; }
 };
 static const ClusterVariant kVariants[] = {
     {512, 8, 1, pick_kernel<512, 8, 1>},  // 0: one octant per CTA, one barrier domain
@@ -494,8 +497,11 @@ static const ClusterVariant kVariants[] = {
     {512, 4, 1, pick_kernel<512, 4, 1>},  // 3
     {512, 2, 2, pick_kernel<512, 2, 2>},  // 4: four octants per CTA, two groups
     {576, 4, 6, pick_kernel<576, 4, 6>},  // 5: two octants per CTA, one group per face quadrant
+    {256, 8, 1, pick_kernel<256, 8, 1>},  // 6: one octant per CTA, two CTAs (two sources) per SM
+    {256, 4, 1, pick_kernel<256, 4, 1>},  // 7: two octants per CTA, two CTAs per SM
+    {256, 2, 1, pick_kernel<256, 2, 1>},  // 8: four octants per CTA, two CTAs per SM
 };
-static int g_variant = 1;
+static int g_variant = 6;
 
 static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, const ClusterVariant& v, int nclusters,
                            size_t smem, cudaStream_t stream) {
@@ -529,7 +535,8 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
   cap = std::min(cap, kQuadrants * (max_radius + 1) * (max_radius + 1)) & ~1;
   // ---- cluster kernel: one CTA per SM with all of the opt-in shared memory ----------------------
-  int cap_cl = (int)(((size_t)max_optin - fixed - 2048) / (2 * sizeof(double)));
+  const int per_cta_cl = (V.ctas_per_sm() == 2) ? per_cta : max_optin;
+  int cap_cl = (int)(((size_t)per_cta_cl - fixed - 2048) / (2 * sizeof(double)));
   cap_cl = std::min(cap_cl, (kQuadrants / V.cluster) * (max_radius + 1) * (max_radius + 1) + 2 * V.groups) & ~1;
   for (int dbg = 0; dbg < 2; ++dbg)
     for (int lls = 0; lls < 4; ++lls) {
@@ -556,6 +563,29 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   info->cluster_size = V.cluster;
   info->grid_max = info->grid_cta + info->clusters * V.cluster;   // both kernels may run concurrently
   return 0;
+}
+
+// Number of b-segments per column for shell r: minimises rounds x (segment length + set-up) for a group
+// of `threads` threads that owns `nq` quadrants, i.e. nq*(r+1) columns.
+static void build_nseg_table(int max_radius, int nq, int threads, std::vector<int>& tab) {
+  tab.assign((size_t)max_radius + 2, 1);
+  for (int r = 1; r <= max_radius; ++r) {
+    const int P1 = r + 1, ncol = nq * P1;
+    long best = -1;
+    int best_n = 1;
+    for (int n = 1; n <= std::max(1, P1 / 2) && n <= 64; ++n) {
+      const long rounds = ((long)ncol * n + threads - 1) / threads;
+      const long cost = rounds * ((P1 + n - 1) / n + 2);
+      if (best < 0 || cost < best) { best = cost; best_n = n; }
+    }
+    tab[r] = best_n;
+  }
+}
+
+void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl) {
+  const ClusterVariant& V = kVariants[g_variant];
+  build_nseg_table(max_radius, kQuadrants, kThreadsCta, cta);
+  build_nseg_table(max_radius, kQuadrants / V.cluster / V.groups, V.threads / V.groups, cl);
 }
 
 static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }

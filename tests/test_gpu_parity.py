@@ -29,9 +29,11 @@ def routing(request, monkeypatch):
         monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
     elif request.param == "cluster":
         monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "0")
+        monkeypatch.setenv("C2B_CLUSTER_MAX_SOURCES", "1000000")
         monkeypatch.setenv("C2B_DEBUG_CLUSTER", "1")
     else:
         monkeypatch.delenv("C2B_CLUSTER_MIN_NBOX", raising=False)
+        monkeypatch.delenv("C2B_CLUSTER_MAX_SOURCES", raising=False)
         monkeypatch.delenv("C2B_DEBUG_CLUSTER", raising=False)
     return request.param
 
