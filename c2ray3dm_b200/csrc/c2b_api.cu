@@ -66,6 +66,8 @@ struct c2b_handle {
   double *d_xh = nullptr, *d_xh_av = nullptr, *d_xh_intermed = nullptr, *d_phih = nullptr;
   float *d_clump = nullptr, *d_lls = nullptr, *d_f32tmp = nullptr;
   double *d_thick = nullptr, *d_thin = nullptr, *d_taucell = nullptr;
+  double *d_taucell_t = nullptr, *d_phih_t = nullptr;   // y-fastest twins for the x-principal quadrants
+  bool taucell_t_dirty = true;
   double2 *d_thick2 = nullptr, *d_logtab = nullptr;
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
   RtLaunchInfo rt;             // shared-memory plane capacities and resident grid sizes
@@ -264,6 +266,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMalloc(&h->d_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_taucell, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell", e);
+  if ((e = cudaMalloc(&h->d_taucell_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell_t", e);
+  if ((e = cudaMalloc(&h->d_phih_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phih_t", e);
   if ((e = cudaMalloc(&h->d_thick2, kTableLen * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_logtab, 128 * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
   {
@@ -319,7 +323,7 @@ void c2b_destroy(c2b_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
-  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
+  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_taucell_t); cudaFree(h->d_phih_t); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
   cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
@@ -627,6 +631,8 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.smem_plane_doubles = h->rt.smem_plane_doubles;
   rp.smem_plane_doubles_cl = h->rt.smem_plane_doubles_cl;
   rp.tau_cell = h->d_taucell;
+  rp.tau_cell_t = h->d_taucell_t;
+  rp.phih_t = h->d_phih_t;
   rp.phih = h->d_phih;
   rp.lls_grid = h->d_lls;
   rp.thick2 = h->d_thick2;
@@ -646,6 +652,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.S_star = h->S_star;
   rp.vol = h->vol;
   rp.use_lls = c.use_LLS;
+  if (const char* env = getenv("C2B_ABLATE")) rp.ablate = atoi(env);
   rp.type_lls = c.type_of_LLS;
   rp.tau_lls = c.sigma_HI * h->coldensh_LLS;
   rp.rmax_lls2 = h->R_max_LLS * h->R_max_LLS;
@@ -668,7 +675,14 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     launch_taucell(h->d_ndens, h->d_xh_av, h->d_taucell, h->ncell, c.sigma_HI * h->dr[0], c.epsilon, h->stream);
     h->launches += 1;
     h->taucell_dirty = false;
+    h->taucell_t_dirty = true;
   }
+  if (h->taucell_t_dirty) {
+    launch_to_yfast(h->d_taucell, h->d_taucell_t, c.mesh, h->stream);
+    h->launches += 1;
+    h->taucell_t_dirty = false;
+  }
+  CU(h, cudaMemsetAsync(h->d_phih_t, 0, h->ncell * sizeof(double), h->stream));
   CU(h, cudaMemsetAsync(h->d_ticket, 0, 2 * sizeof(unsigned int), h->stream));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   if (nwork_cl > 0) {  // long traces first: one cluster per source, planes in shared memory
@@ -686,6 +700,11 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   if (nwork > 0) {
     const int grid = std::min(h->rt.grid_cta, nwork);
     launch_raytrace(rp, grid, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+  }
+  if (nwork > 0 || nwork_cl > 0) {
+    launch_add_from_yfast(h->d_phih, h->d_phih_t, c.mesh, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
   }
@@ -817,6 +836,7 @@ int c2b_global_pass(c2b_handle* h, double dt, c2b_global_report* rep) {
   launch_chemistry(cp, h->chem_blocks, h->stream);
   h->launches += 1;
   h->taucell_dirty = false;  // the chemistry kernel wrote tau_cell from the new xh_av
+  h->taucell_t_dirty = true;
   CU(h, cudaEventRecord(h->ev[1], h->stream));
   if (int rc = fetch_stats(h)) return rc;
   float ms = 0.f;

@@ -28,6 +28,8 @@ struct RtParams {
   int smem_plane_doubles_cl;  // same for a CTA of the cluster kernel
   const double* tau_cell;   // sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens per cell
   double* phih;             // evolve_data.F90:40
+  const double* tau_cell_t; // y-fastest twins used by the x-principal quadrants
+  double* phih_t;
   const float* lls_grid;    // LLS.F90:81 (type_of_LLS == 2) or nullptr
   const double2* thick2;    // stellar_photo_thick_table as (value, forward difference) pairs
   const double* thin;       // stellar_photo_thin_table(0:NumTau,1)
@@ -45,6 +47,7 @@ struct RtParams {
   double* coldens_dbg;      // optional full coldensh_out grid (debug/parity), or nullptr
   double S_star, dr[3], vol;
   int use_lls, type_lls;
+  int ablate;               // diagnostic bit mask (C2B_ABLATE): 1 = no atomics, 2 = no rate look-ups (timing studies only)
   double tau_lls;           // sigma_HI*coldensh_LLS
   double rmax_lls2;
   double sigma_HI, inv_sigma, inv_sigma_dr0, fourpi_over_sigma;
@@ -104,6 +107,8 @@ void launch_finalize_partials(const double* partials, int nblocks, double* out /
                               cudaStream_t stream);
 void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream);
 void launch_to_f32(const double* in, float* out, size_t n, cudaStream_t stream);
+void launch_to_yfast(const double* in, double* out, const int n[3], cudaStream_t stream);
+void launch_add_from_yfast(double* acc, const double* twin, const int n[3], cudaStream_t stream);
 int chemistry_blocks();
 
 // ---- rate tables (rad_ini) -----------------------------------------------------------------------

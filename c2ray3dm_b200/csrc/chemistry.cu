@@ -175,6 +175,39 @@ __global__ void to_f32_kernel(const double* in, float* out, size_t n) {
     out[c] = (float)in[c];
 }
 
+// y-fastest twin of an x-fastest grid: out[(x*n2 + z)*n1 + y] = in[(z*n1 + y)*n0 + x]  (32x32 tiles in x,y)
+__global__ void to_yfast_kernel(const double* __restrict__ in, double* __restrict__ out, int n0, int n1, int n2) {
+  __shared__ double tile[32][33];
+  const int z = blockIdx.z;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + threadIdx.x, y = y0 + j;
+    if (x < n0 && y < n1) tile[j][threadIdx.x] = in[((size_t)z * n1 + y) * n0 + x];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + j, y = y0 + threadIdx.x;
+    if (x < n0 && y < n1) out[((size_t)x * n2 + z) * n1 + y] = tile[threadIdx.x][j];
+  }
+}
+
+// acc[(z*n1 + y)*n0 + x] += twin[(x*n2 + z)*n1 + y]: folds the rates the x-principal quadrants
+// accumulated in the y-fastest twin back into phih_grid
+__global__ void add_from_yfast_kernel(double* __restrict__ acc, const double* __restrict__ twin, int n0, int n1, int n2) {
+  __shared__ double tile[32][33];
+  const int z = blockIdx.z;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + j, y = y0 + threadIdx.x;
+    if (x < n0 && y < n1) tile[threadIdx.x][j] = twin[((size_t)x * n2 + z) * n1 + y];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int x = x0 + threadIdx.x, y = y0 + j;
+    if (x < n0 && y < n1) acc[((size_t)z * n1 + y) * n0 + x] += tile[j][threadIdx.x];
+  }
+}
+
 __global__ void dfma_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
   double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
@@ -210,6 +243,15 @@ void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t 
 }
 void launch_to_f32(const double* in, float* out, size_t n, cudaStream_t stream) {
   to_f32_kernel<<<chemistry_blocks(), 256, 0, stream>>>(in, out, n);
+}
+
+void launch_to_yfast(const double* in, double* out, const int n[3], cudaStream_t stream) {
+  dim3 grid((n[0] + 31) / 32, (n[1] + 31) / 32, n[2]), block(32, 8);
+  to_yfast_kernel<<<grid, block, 0, stream>>>(in, out, n[0], n[1], n[2]);
+}
+void launch_add_from_yfast(double* acc, const double* twin, const int n[3], cudaStream_t stream) {
+  dim3 grid((n[0] + 31) / 32, (n[1] + 31) / 32, n[2]), block(32, 8);
+  add_from_yfast_kernel<<<grid, block, 0, stream>>>(acc, twin, n[0], n[1], n[2]);
 }
 
 double measure_dfma_rate(cudaStream_t stream) {

@@ -47,6 +47,10 @@ namespace {
 
 constexpr int kThreadsCta = 256;   // one CTA per source
 constexpr int kQuadrants = 24;
+#ifndef C2B_CTA_PER_SM
+#define C2B_CTA_PER_SM 2
+#endif
+constexpr int kCtaPerSm = C2B_CTA_PER_SM;   // resident CTAs per SM of the one-CTA-per-source kernel
 
 // max/min of two NON-NEGATIVE doubles through their bit patterns (integer order == numeric order there);
 // avoids the NaN-propagating DSETP.MAX/FSEL/LOP3 sequence fmax() and ?: compile to.
@@ -148,7 +152,7 @@ __device__ __forceinline__ int wrap(int x, int n) {
 // kGroups: the CTA's warps form kGroups independent groups, each owning kNq/kGroups quadrants and its own
 // named barrier, so a group waiting for its shell to complete does not idle the others.
 template <int kT, int kCluster, int kGroups, int kLls, bool kDebug>
-__global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtParams P) {
+__global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm : 2) : 1) raytrace_kernel(RtParams P) {
   constexpr int kNq = kQuadrants / kCluster;        // face quadrants handled by this CTA
   constexpr int kNqg = kNq / kGroups;               // ... by one warp group
   constexpr int kTg = kT / kGroups;                 // threads per group
@@ -282,9 +286,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
           const int srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
           const int srcA = (p == 2) ? src1 : src0;
           const int srcB = (p == 0) ? src1 : src2;
-          const unsigned strP = (p == 0) ? st2 : (p == 1 ? st1 : st0);
-          const unsigned strA = (p == 2) ? st1 : st0;
-          const unsigned strideB = (p == 0) ? st1 : st2;
+          // x-principal quadrants walk planes of constant x: they use the y-fastest twins of the grids
+          // (index (x*n2 + z)*n1 + y) so that a warp's lanes (consecutive a = y) stay contiguous in memory
+          const unsigned strP = (p == 0) ? st2 : (p == 1 ? st1 : (unsigned)n1 * (unsigned)n2);
+          const unsigned strA = 1u;
+          const unsigned strideB = (p == 0) ? st1 : (p == 1 ? st2 : (unsigned)n1);
+          const double* __restrict__ g_tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
+          double* __restrict__ g_phih = (p == 2) ? P.phih_t : P.phih;
           const double dr2P = (p == 0) ? dr2_2 : (p == 1 ? dr2_1 : dr2_0);
           const double dr2A = (p == 2) ? dr2_1 : dr2_0;
           const double dr2B = (p == 0) ? dr2_1 : dr2_2;
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
           // software pipeline: the plane and grid values of the next cell are requested one iteration ahead
           unsigned cell_next = base + (unsigned)posB * strideB;
           double tau_cell_next = 0.0, c_own_next = 0.0, c_lane0_next = 0.0;
-          if (nact > 0) tau_cell_next = P.tau_cell[cell_next];
+          if (nact > 0) tau_cell_next = g_tau[cell_next];
           if (a_in && nup > 0) c_own_next = pown[0];
           if (lane == 0 && a >= 1 && nup > 0) c_lane0_next = pown[-1];
           double bd = (double)b0;
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
             else if (posB >= nB) { posB -= nB; cn -= dwrap; }
             cell_next = (unsigned)cn;
             c_own_next = 0.0;
-            if (k + 1 < nact) tau_cell_next = P.tau_cell[cell_next];
+            if (k + 1 < nact) tau_cell_next = g_tau[cell_next];
             if (k + 1 < nup) {
               if (a_in) c_own_next = pown[0];
               if (lane == 0 && a >= 1) c_lane0_next = pown[-1];
@@ -349,6 +357,13 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
             }
             if (active) {
               bool stop = false;
+              // x-fastest index of the cell, only for the grids that have no y-fastest twin
+              unsigned xcell = 0;
+              if ((kDebug || kLls == 2) && p == 2) {
+                const unsigned t = cell;                    // (x*n2 + z)*n1 + y
+                const unsigned yy = t % (unsigned)n1, xz = t / (unsigned)n1;
+                xcell = (xz % (unsigned)n2) * st2 + yy * st1 + xz / (unsigned)n2;
+              }
               // cinterp, column_density.f90:108-171, with a common denominator
               const double ub = bd * inv_r;  // 1-dy
               const double va = 1.0 - ua, vb = 1.0 - ub;
@@ -372,7 +387,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
               if (kLls == 3) {  // evolve_point.F90:186-196
                 if (dist2 > P.rmax_lls2) stop = true;
               } else if (kLls == 2) {
-                tau_in = fma((double)P.lls_grid[cell] * P.sigma_HI, pathc, tau_in);
+                tau_in = fma((double)P.lls_grid[(p == 2) ? xcell : cell] * P.sigma_HI, pathc, tau_in);
               } else if (kLls == 1) {
                 tau_in = fma(P.tau_lls, pathc, tau_in);
               }
@@ -381,13 +396,14 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? 2 : 1) raytrace_kernel(RtPar
               *pout = tau_out;
               const bool owner = own_col && (b > 0 || sb > 0) && (p == 0 || b < r);
               if (owner) {
-                if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
-                if (!stop && normflux > 0.0) {
+                if (kDebug) P.coldens_dbg[(p == 2) ? xcell : cell] = tau_out * P.inv_sigma;
+                if (!stop && normflux > 0.0 && !(P.ablate & 2)) {
                   double phi_all, phi_out;
                   photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
                   const double inv_vol = fast_rcp(volfac);
                   const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
-                  if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);  // :283-284
+                  if (photo_cell != 0.0 && !(P.ablate & 1)) atomicAdd(&g_phih[cell], photo_cell);  // :283-284
+                  if (P.ablate & 1) loss += photo_cell * 1e-300;
                   // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
                   if (loss_col || (sb * b == lrB) || (sb * b == -llB))
                     loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
@@ -531,11 +547,11 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   const ClusterVariant& V = kVariants[g_variant];
   const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
   // ---- single-CTA kernel: two CTAs per SM share the opt-in shared memory ----------------------
-  const int per_cta = std::min(max_optin, sm_total / 2 - 2048);
+  const int per_cta = std::min(max_optin, sm_total / kCtaPerSm - 2048);
   int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
   cap = std::min(cap, kQuadrants * (max_radius + 1) * (max_radius + 1)) & ~1;
   // ---- cluster kernel: one CTA per SM with all of the opt-in shared memory ----------------------
-  const int per_cta_cl = (V.ctas_per_sm() == 2) ? per_cta : max_optin;
+  const int per_cta_cl = (V.ctas_per_sm() == 2) ? std::min(max_optin, sm_total / 2 - 2048) : max_optin;
   int cap_cl = (int)(((size_t)per_cta_cl - fixed - 2048) / (2 * sizeof(double)));
   cap_cl = std::min(cap_cl, (kQuadrants / V.cluster) * (max_radius + 1) * (max_radius + 1) + 2 * V.groups) & ~1;
   for (int dbg = 0; dbg < 2; ++dbg)
