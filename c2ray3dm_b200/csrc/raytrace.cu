@@ -48,7 +48,7 @@ namespace {
 constexpr int kThreadsCta = 256;   // one CTA per source
 constexpr int kQuadrants = 24;
 #ifndef C2B_CTA_PER_SM
-#define C2B_CTA_PER_SM 2
+#define C2B_CTA_PER_SM 3
 #endif
 constexpr int kCtaPerSm = C2B_CTA_PER_SM;   // resident CTAs per SM of the one-CTA-per-source kernel
 
