@@ -33,6 +33,9 @@ import numpy as np  # noqa: E402
 METRIC = "cell-source raytrace updates/s"
 UNIT = "updates/s"
 B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 + xh_av 8 + phih RMW 16
+# dram__bytes_read.sum + dram__bytes_write.sum of one raytrace_kernel launch on this workload divided by
+# the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r1_summary.txt)
+NCU_DRAM_BYTES_PER_UPDATE = 28.8
 YEAR = 3.15576e7
 
 
@@ -301,7 +304,11 @@ def run_ours(args):
                 "phase_ms_per_step": {"raytrace": ms_rt / args.steps, "allreduce": ms_ar / args.steps,
                                       "chemistry": ms_chem / args.steps, "device_total": ms_dev / args.steps},
                 "roofline": {"kernel": "raytrace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": NCU_DRAM_BYTES_PER_UPDATE * upd_rank / max(1, niter) if args.mesh == 256 else None,
+                             "traffic_note": "bytes per launch = %.1f B/update (ncu dram bytes of one launch of this "
+                                             "workload, profiles/) x updates per launch" % NCU_DRAM_BYTES_PER_UPDATE,
+                             "algorithmic_bytes_per_launch": B_RT * upd_rank / max(1, niter),
                              "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind,
                              "algorithmic_bytes_per_update": B_RT,
                              "note": "FP64-issue bound expected to bind first (SURVEY 8d)"},

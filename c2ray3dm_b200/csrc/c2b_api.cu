@@ -626,6 +626,9 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     rp.lim[d][1] = h->lim[d][1];
     rp.dr[d] = h->dr[d];
   }
+  for (int d = 0; d < 3; ++d) rp.dr2[d] = h->dr[d] * h->dr[d];
+  rp.tau_stop = c.max_coldensh * c.sigma_HI;
+  rp.vol_cell = h->dr[0] * h->dr[1] * h->dr[2];
   rp.subboxsize = c.subboxsize;
   rp.plane_stride = h->plane_stride;
   rp.smem_plane_doubles = h->rt.smem_plane_doubles;

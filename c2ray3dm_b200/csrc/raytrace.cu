@@ -183,9 +183,6 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
   double* gbuf1 = gbuf0 + gplane;
   const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
   const unsigned st0 = 1u, st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;
-  const double dr2_0 = P.dr[0] * P.dr[0], dr2_1 = P.dr[1] * P.dr[1], dr2_2 = P.dr[2] * P.dr[2];
-  const double tau_stop = P.max_coldensh * P.sigma_HI;   // coldensh_in > max_coldensh, evolve_point.F90:201
-  const double vol_cell = P.dr[0] * P.dr[1] * P.dr[2];   // vol_ph of the source cell, :153
   int pass_parity = 0;
 
   for (;;) {
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
               double phi_all, phi_out;
               photo_rates(0.0, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
               // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
-              const double photo_cell = phi_all * fast_rcp(vol_cell * tau_cell * P.inv_sigma_dr0);
+              const double photo_cell = phi_all * fast_rcp(P.vol_cell * tau_cell * P.inv_sigma_dr0);
               if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);
             }
           }
@@ -293,19 +290,26 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
           const unsigned strideB = (p == 0) ? st1 : (p == 1 ? st2 : (unsigned)n1);
           const double* __restrict__ g_tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
           double* __restrict__ g_phih = (p == 2) ? P.phih_t : P.phih;
-          const double dr2P = (p == 0) ? dr2_2 : (p == 1 ? dr2_1 : dr2_0);
-          const double dr2A = (p == 2) ? dr2_1 : dr2_0;
-          const double dr2B = (p == 0) ? dr2_1 : dr2_2;
+          const double dr2P = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
+          const double dr2A = (p == 2) ? P.dr2[1] : P.dr2[0];
+          const double dr2B = (p == 0) ? P.dr2[1] : P.dr2[2];
           const unsigned base = (unsigned)wrap(srcP + sp * r, nP) * strP + (unsigned)wrap(srcA + sa * a, nA) * strA;
           int posB = srcB + sb * b0;
           if (posB < 0) posB += nB;
           else if (posB >= nB) posB -= nB;
+          // the walk along b crosses the periodic boundary at most once: after kwrap more steps
+          const int kwrap = (sb > 0) ? (nB - 1 - posB) : posB;
           // column-level geometry
           const double ua = (double)a * inv_r;   // 1-dx of cinterp (a==r gives 1 to an ulp; the cells it would exclude read as 0)
           const double ca2 = (double)(r * r + a * a);
           const double dist_col = dr2P * (double)(r * r) + dr2A * (double)(a * a);
           // ownership pieces that do not depend on b (see header comment)
           const bool own_col = (a > 0 || sa > 0) && (p != 2 || a < r);
+          // owned rows of this column: b in [own_lo, own_hi] (b==0 belongs to the sb>0 quadrant; b==r belongs
+          // to the z-principal quadrant)
+          const int own_lo = own_col ? ((sb > 0) ? 0 : 1) : 0x7fffffff;
+          const int own_hi = (p == 0) ? r : r - 1;
+          const int loss_b = (sb > 0) ? lrB : llB;     // row on the subbox boundary (any row if the column is)
           const bool loss_col = (sp > 0 ? r == lrP : r == llP) || (sa * a == lrA) || (sa * a == -llA);
           const bool a_in = a <= r - 1;           // column a exists in plane r-1
           const int blast = min(bmax, r - 1);     // last b with an upstream value in this column
@@ -326,7 +330,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
           if (a_in && nup > 0) c_own_next = pown[0];
           if (lane == 0 && a >= 1 && nup > 0) c_lane0_next = pown[-1];
           double bd = (double)b0;
-          const int dcell = sb * (int)strideB, dwrap = (int)strideB * nB;
+          const int dcell = sb * (int)strideB;
+          const int dcell_wrap = dcell - sb * (int)strideB * nB;   // step that crosses the boundary
           for (int k = 0; k < seglen; ++k) {
             const int b = b0 + k;
             const bool active = k < nact;
@@ -342,11 +347,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
             const double tau_cell = tau_cell_next;
             // advance to row b+1 and request its inputs
             pown += r;
-            posB += sb;
-            int cn = (int)cell + dcell;
-            if (posB < 0) { posB += nB; cn += dwrap; }
-            else if (posB >= nB) { posB -= nB; cn -= dwrap; }
-            cell_next = (unsigned)cn;
+            cell_next = (unsigned)((int)cell + ((k == kwrap) ? dcell_wrap : dcell));
             c_own_next = 0.0;
             if (k + 1 < nact) tau_cell_next = g_tau[cell_next];
             if (k + 1 < nup) {
@@ -391,21 +392,20 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
               } else if (kLls == 1) {
                 tau_in = fma(P.tau_lls, pathc, tau_in);
               }
-              if (tau_in > tau_stop) stop = true;                          // :201
+              if (tau_in > P.tau_stop) stop = true;                          // :201
               const double tau_out = fma(tau_cell, pathc, tau_in);         // :247-248
               *pout = tau_out;
-              const bool owner = own_col && (b > 0 || sb > 0) && (p == 0 || b < r);
+              const bool owner = (b >= own_lo) && (b <= own_hi);
               if (owner) {
                 if (kDebug) P.coldens_dbg[(p == 2) ? xcell : cell] = tau_out * P.inv_sigma;
-                if (!stop && normflux > 0.0 && !(P.ablate & 2)) {
+                if (!stop && normflux > 0.0) {
                   double phi_all, phi_out;
                   photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
                   const double inv_vol = fast_rcp(volfac);
                   const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
-                  if (photo_cell != 0.0 && !(P.ablate & 1)) atomicAdd(&g_phih[cell], photo_cell);  // :283-284
-                  if (P.ablate & 1) loss += photo_cell * 1e-300;
+                  if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);  // :283-284
                   // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
-                  if (loss_col || (sb * b == lrB) || (sb * b == -llB))
+                  if (loss_col || b == loss_b)
                     loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
                 }
               }
