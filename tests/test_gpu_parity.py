@@ -406,3 +406,37 @@ def test_full_box_update_count_512_quirk():
     ph = e.phih_grid
     assert np.count_nonzero(ph) == 511 ** 3
     e.close()
+
+
+def test_nbody_test_history_single_source(gpu_tables):
+    """BASELINE config 1 in miniature: the nbody_test problem (uniform mean density at z=9, 100/h Mpc box,
+    LLS type 1, xh=2e-4, T=1e4 K, one 1e57 s^-1 source), 4 consecutive steps with cosmo_evol between them;
+    with one source conv_criterion is 0, so only the 1e-4 test on the sums ends the outer loop"""
+    from c2ray3dm_b200 import synthetic as syn, constants as K
+    N = 40
+    p = make_problem(N, nsrc=1, seed=3, state="neutral", use_LLS=True, dens="uniform", srcpos=[[17, 20, 23]])
+    p["normflux"] = np.array([1e57 / 1e48])
+    o = setup_oracle(p, tables=gpu_tables)
+    e = setup_gpu(p, tables=gpu_tables)
+    ndens = p["ndens"].copy()
+    dr, vol = p["dr"].copy(), p["vol"]
+    dt = 1e6 * 3.15576e7
+    for step in range(4):
+        zf = 1.0 + 2e-3 * (step + 1)
+        zf3 = zf * zf * zf
+        dr, vol = dr * zf, vol * zf3
+        ndens = (ndens.astype(np.float64) / zf3).astype(np.float32)
+        o.set_density(ndens)
+        o.set_geometry(dr, vol)
+        o.set_lls(True, 1, syn.lls_coldens(dr[0], 9.0), None, 0.0)
+        e.cosmo_evol(zf)
+        e.set_LLS(coldensh_LLS=syn.lls_coldens(dr[0], 9.0))
+        ro = o.evolve3D(dt)
+        rg = e.evolve3D(step * dt, dt)
+        assert ro.conv_criterion == 0 and rg.conv_criterion == 0
+        assert rg.niter == ro.niter and rg.converged == ro.converged
+        assert list(rg.sum_nbox_all[1:rg.niter + 1]) == list(ro.sum_nbox_all[1:ro.niter + 1])
+        np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+        _rates_close(e.phih_grid, o.phih)
+        assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
+    e.close()
