@@ -10,8 +10,9 @@ iterations of {ray-trace every source, reduce the rate grid over ranks, per-cell
 
 Workload (N=1): BASELINE.json configs[2] -- synthetic log-normal density 256^3, 10^4 sources at the
 density peaks, clumping grid on, LLS on, mid-reionization bubble state (mean ionized fraction 0.54: spheres of up to
-25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling): every GPU
-holds the full grids and traces its round-robin share (master_slave.F90:85), the partial rate grids are
+25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling) and the bubble
+radius shrinks by N^(-1/3) so that the ionized volume, and with it the work per GPU, stays comparable: every
+GPU holds the full grids and traces its round-robin share (master_slave.F90:85), the partial rate grids are
 summed with ncclAllReduce (evolve.F90:599-602).
 
 The reference is Fortran and cannot be built in this image (no Fortran compiler), so the reference arm
@@ -65,7 +66,7 @@ def load_peaks():
 
 
 def build_workload(mesh, nsrc_total, bubble):
-    """inputs of configs[2]/[3], deterministic"""
+    """inputs of configs[2]/[3], deterministic; `bubble` = radius of the brightest source's sphere"""
     from c2ray3dm_b200 import synthetic as syn
     zred = 9.0
     seed = 20240607 if mesh == 256 else (20240608 if mesh == 512 else 20240600 + mesh)
@@ -150,20 +151,20 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    w = build_workload(args.mesh, args.nsrc * args.gpus, args.bubble)
+    w = build_workload(args.mesh, args.nsrc * args.gpus, args.bubble * args.gpus ** (-1.0 / 3.0))
     nsample = args.cpu_sample or max(cores * 4, 64)
     rates, secs, upd = [], [], []
     desc = ""
+    # size the sample towards ~10-20 s of CPU work per step (the whole run stays within minutes)
+    v, desc, s, u = cpu_sample(w, args.mesh, nsample, cores)
+    if not args.cpu_sample:
+        nsample = int(min(len(w["normflux"]), max(8, nsample * 12.0 / max(s, 1e-3))))
     for i in range(args.warmup + args.steps):
-        if i == 1 and args.warmup > 1:
-            pass
         v, desc, s, u = cpu_sample(w, args.mesh, nsample, cores)
         if i >= args.warmup:
             rates.append(v)
             secs.append(s)
             upd.append(u)
-        if i == 0 and s > 60:   # keep the whole run within minutes
-            nsample = max(8, int(nsample * 30 / s))
     value = float(np.sum(upd) / np.sum([u / r for u, r in zip(upd, rates)]))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
@@ -179,8 +180,8 @@ def run_reference(args):
 
 def workload_config(args):
     return {"workload": "synthetic lognormal density %d^3, %d sources/GPU at density peaks, clumping grid (type 5), "
-                        "LLS type 1, mid-reionization bubble state r<=%g cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
-                            args.mesh, args.nsrc, args.bubble, args.dt_myr),
+                        "LLS type 1, mid-reionization bubble state r<=%.1f cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
+                            args.mesh, args.nsrc, args.bubble * args.gpus ** (-1.0 / 3.0), args.dt_myr),
             "mesh": args.mesh, "sources_total": args.nsrc * args.gpus, "parallelism": "source-sharded x%d" % args.gpus,
             "l2": "grids (ndens+xh_av+phih = %.0f MB) exceed the 126 MB L2" % (20 * args.mesh ** 3 / 1e6)
             if args.mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
@@ -203,7 +204,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mesh = args.mesh
-    w = build_workload(mesh, args.nsrc * world, args.bubble)
+    w = build_workload(mesh, args.nsrc * world, args.bubble * world ** (-1.0 / 3.0))
     dt = args.dt_myr * 1e6 * YEAR
 
     e = Evolve(mesh, device=local, rank=rank, nranks=world, type_of_clumping=5, use_LLS=True, type_of_LLS=1)

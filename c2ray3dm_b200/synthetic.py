@@ -80,16 +80,21 @@ def bubble_state(shape, srcpos, radius_cells, x_in=1.0 - 1e-4, x_out=K.xh_initia
     every source, neutral elsewhere."""
     n3, n2, n1 = shape
     xh = np.full(shape, x_out, dtype=np.float64)
+    flat = xh.reshape(-1)
     radius = np.broadcast_to(np.asarray(radius_cells, dtype=np.float64), (len(srcpos),))
+    cache = {}
     for (i, j, k), r in zip(np.asarray(srcpos), radius):
         ri = int(np.ceil(r))
-        di = np.arange(-ri, ri + 1)
-        dz, dy, dx = np.meshgrid(di, di, di, indexing="ij")
-        m = dx * dx + dy * dy + dz * dz <= r * r
-        xi = (i - 1 + dx[m]) % n1
-        yj = (j - 1 + dy[m]) % n2
-        zk = (k - 1 + dz[m]) % n3
-        xh[zk, yj, xi] = x_in
+        if ri not in cache:
+            di = np.arange(-ri, ri + 1, dtype=np.int32)
+            dz, dy, dx = np.meshgrid(di, di, di, indexing="ij")
+            d2 = (dx * dx + dy * dy + dz * dz).reshape(-1)
+            order = np.argsort(d2, kind="stable")
+            cache[ri] = (dx.reshape(-1)[order], dy.reshape(-1)[order], dz.reshape(-1)[order], d2[order])
+        dx, dy, dz, d2 = cache[ri]
+        n = int(np.searchsorted(d2, r * r, side="right"))      # offsets are sorted by distance
+        idx = (((k - 1 + dz[:n]) % n3) * n2 + ((j - 1 + dy[:n]) % n2)) * n1 + ((i - 1 + dx[:n]) % n1)
+        flat[idx] = x_in
     return xh
 
 
