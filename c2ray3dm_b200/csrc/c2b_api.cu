@@ -693,6 +693,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     rc.work = d_work_cl;
     rc.nwork = nwork_cl;
     rc.ticket = h->d_ticket + 1;
+    rc.scratch = h->d_scratch + raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt.grid_cta;
     const int ncl = std::min(h->rt.clusters, nwork_cl);
     if (launch_raytrace_cluster(rc, ncl, h->stream)) {
       CU(h, cudaGetLastError());

@@ -577,7 +577,9 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   if (e != cudaSuccess) return (int)e;
   info->clusters = std::max(1, nclusters);
   info->cluster_size = V.cluster;
-  info->grid_max = info->grid_cta + info->clusters * V.cluster;   // both kernels may run concurrently
+  // scratch slots of 2*24*S*S doubles: one per resident CTA of the single-CTA kernel plus one per resident
+  // cluster (its CTAs share a slot: 24/cluster quadrants each)
+  info->grid_max = info->grid_cta + info->clusters;
   return 0;
 }
 

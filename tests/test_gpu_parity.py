@@ -440,3 +440,16 @@ def test_nbody_test_history_single_source(gpu_tables):
         _rates_close(e.phih_grid, o.phih)
         assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
     e.close()
+
+
+def test_device_pointers_and_probes():
+    """harness entry points: device pointers by name, DFMA probe, synchronize"""
+    p = make_problem(12, nsrc=1, seed=2)
+    e = setup_gpu(p)
+    for name in (b"ndens", b"xh", b"xh_av", b"xh_intermed", b"phih"):
+        assert e.L.c2b_dev_ptr(e.h, name)
+    assert not e.L.c2b_dev_ptr(e.h, b"nonsense")
+    e.synchronize()
+    rate = e.measure_dfma_rate()
+    assert 5e12 < rate < 5e13      # B200: ~1.8e13 FP64 FMA instructions/s
+    e.close()
