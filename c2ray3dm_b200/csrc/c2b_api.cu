@@ -784,8 +784,17 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       small.insert(small.end(), large.begin(), large.end());
       large.clear();
     }
-    std::stable_sort(large.begin(), large.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
-    std::stable_sort(small.begin(), small.end(), [&](int x, int y) { return h->nbox_pred[x] > h->nbox_pred[y]; });
+    // longest predicted trace first (counting sort on nbox, stable within a bucket)
+    auto by_nbox_desc = [&](std::vector<int>& v) {
+      int mx = 0;
+      for (int w : v) mx = std::max(mx, h->nbox_pred[w]);
+      std::vector<std::vector<int>> bucket((size_t)mx + 1);
+      for (int w : v) bucket[(size_t)h->nbox_pred[w]].push_back(w);
+      v.clear();
+      for (int b = mx; b >= 0; --b) v.insert(v.end(), bucket[(size_t)b].begin(), bucket[(size_t)b].end());
+    };
+    by_nbox_desc(large);
+    by_nbox_desc(small);
     if (!small.empty())
       CU(h, cudaMemcpyAsync(h->d_work, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!large.empty())

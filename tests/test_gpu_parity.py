@@ -453,3 +453,27 @@ def test_device_pointers_and_probes():
     rate = e.measure_dfma_rate()
     assert 5e12 < rate < 5e13      # B200: ~1.8e13 FP64 FMA instructions/s
     e.close()
+
+
+def test_full_box_trace_spills_planes_to_global(gpu_tables):
+    """N=100, one source, ionized gas, no LLS: the trace covers the whole periodic box (10 subboxes,
+    r up to 50), so the shell planes outgrow shared memory in both ray-trace kernels and live in the
+    global scratch; compared cell by cell with the oracle"""
+    p = make_problem(100, nsrc=1, seed=23, state="ionized", use_LLS=False, srcpos=[[97, 3, 50]], flux=1e9)
+    e = setup_gpu(p, tables=gpu_tables)
+    e.begin_step()
+    o = setup_oracle(p, tables=gpu_tables)
+    o.xh_av[...] = p["xh"]
+    o.set_rates_to_zero()
+    rr = o.do_source(1)
+    cd, ph, nbox, loss = e.trace_source_debug(1)
+    assert nbox == rr.nbox == 10
+    assert rr.updates == 100 ** 3
+    assert np.array_equal(cd == 0, o.coldensh_out == 0)
+    np.testing.assert_allclose(cd, o.coldensh_out, rtol=1e-11, atol=0)
+    _rates_close(ph, o.phih)
+    assert loss == pytest.approx(rr.photon_loss_src, rel=RATE_RTOL)
+    g = e.pass_all_sources()
+    assert g.updates == 100 ** 3 and g.sum_nbox_all == 10
+    _rates_close(e.phih_grid, o.phih)
+    e.close()
