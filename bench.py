@@ -37,6 +37,7 @@ B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 +
 # dram__bytes_read.sum + dram__bytes_write.sum of one raytrace_kernel launch on this workload divided by
 # the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r1_summary.txt)
 NCU_DRAM_BYTES_PER_UPDATE = 28.8
+FP64_INSTR_PER_UPDATE = 91  # FP64-pipe instructions in the inner loop of raytrace_kernel (static SASS, scripts/sass_loop.py)
 YEAR = 3.15576e7
 
 
@@ -313,8 +314,10 @@ def run_ours(args):
                              "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind,
                              "algorithmic_bytes_per_update": B_RT,
                              "note": "FP64-issue bound expected to bind first (SURVEY 8d)"},
-                "fp64": {"dfma_per_s_measured": dfma,
-                         "updates_per_s_per_gpu_raytrace": upd_rank / (ms_rt_max * 1e-3) if ms_rt_max > 0 else 0.0},
+                "fp64": {"dfma_per_s_measured": dfma, "fp64_instr_per_update_sass": FP64_INSTR_PER_UPDATE,
+                         "updates_per_s_per_gpu_raytrace": upd_rank / (ms_rt_max * 1e-3) if ms_rt_max > 0 else 0.0,
+                         "frac_of_fp64_issue_bound": (upd_rank / (ms_rt_max * 1e-3)) * FP64_INSTR_PER_UPDATE / dfma
+                         if ms_rt_max > 0 and dfma > 0 else None},
                 "clocks": sampler.summary(),
                 "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -54,9 +54,6 @@ constexpr int kCtaPerSm = C2B_CTA_PER_SM;   // resident CTAs per SM of the one-C
 
 // max/min of two NON-NEGATIVE doubles through their bit patterns (integer order == numeric order there);
 // avoids the NaN-propagating DSETP.MAX/FSEL/LOP3 sequence fmax() and ?: compile to.
-__device__ __forceinline__ double pos_max(double x, double y) {
-  return __longlong_as_double(max(__double_as_longlong(x), __double_as_longlong(y)));
-}
 __device__ __forceinline__ double pos_min(double x, double y) {
   return __longlong_as_double(min(__double_as_longlong(x), __double_as_longlong(y)));
 }
@@ -182,7 +179,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
   double* gbuf0 = P.scratch + ((size_t)blockIdx.x * kGroups + grp) * 2 * gplane;
   double* gbuf1 = gbuf0 + gplane;
   const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
-  const unsigned st0 = 1u, st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;
+  const unsigned st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;   // x-fastest strides of y and z
   int pass_parity = 0;
 
   for (;;) {
@@ -382,11 +379,8 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
               const double q2 = ca2 + b2;
               const double rs = fast_rsqrt(q2);
               const double pathc = q2 * rs * inv_r;                        // sqrt(1+(a^2+b^2)/r^2)
-              const double dist2 = fma(dr2B, b2, dist_col);                // evolve_point.F90:170-174
-              // vol_ph = 4*pi*dist2*path ; rate = phi_all/(vol_ph*nHI) = phi_all/volfac
-              const double volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
               if (kLls == 3) {  // evolve_point.F90:186-196
-                if (dist2 > P.rmax_lls2) stop = true;
+                if (fma(dr2B, b2, dist_col) > P.rmax_lls2) stop = true;
               } else if (kLls == 2) {
                 tau_in = fma((double)P.lls_grid[(p == 2) ? xcell : cell] * P.sigma_HI, pathc, tau_in);
               } else if (kLls == 1) {
@@ -401,6 +395,9 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
                 if (!stop && normflux > 0.0) {
                   double phi_all, phi_out;
                   photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
+                  // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI) = phi_all/volfac
+                  const double dist2 = fma(dr2B, b2, dist_col);
+                  const double volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
                   const double inv_vol = fast_rcp(volfac);
                   const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
                   if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);  // :283-284
