@@ -87,6 +87,7 @@ struct c2b_handle {
   int* h_nbox = nullptr;      // pinned
   double* h_loss = nullptr;   // pinned
   std::vector<int> work;      // 0-based source indices of this rank
+  std::vector<int> work_morton;  // the same indices in Z-order of their mesh position (L2 locality of concurrent traces)
   std::vector<int> srcpos;
   double sum_normflux = 0.0, S_star = 0.0;
   // ray-trace launch resources
@@ -508,6 +509,29 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
   h->nwork = (int)h->work.size();
   h->nbox_pred.assign((size_t)NumSrc, 0);
+  {
+    // Z-order (Morton) key of the source cell: consecutive work items are spatial neighbours, so the traces
+    // in flight at the same time share grid lines in L2
+    auto spread = [](unsigned long long v) {
+      v &= 0x1fffffULL;
+      v = (v | (v << 32)) & 0x1f00000000ffffULL;
+      v = (v | (v << 16)) & 0x1f0000ff0000ffULL;
+      v = (v | (v << 8)) & 0x100f00f00f00f00fULL;
+      v = (v | (v << 4)) & 0x10c30c30c30c30c3ULL;
+      v = (v | (v << 2)) & 0x1249249249249249ULL;
+      return v;
+    };
+    std::vector<std::pair<unsigned long long, int>> keyed;
+    keyed.reserve(h->work.size());
+    for (int w : h->work) {
+      const unsigned long long k = spread((unsigned)(srcpos[3 * w] - 1) >> 3) | (spread((unsigned)(srcpos[3 * w + 1] - 1) >> 3) << 1) |
+                                   (spread((unsigned)(srcpos[3 * w + 2] - 1) >> 3) << 2);
+      keyed.emplace_back(k, w);
+    }
+    std::stable_sort(keyed.begin(), keyed.end());
+    h->work_morton.clear();
+    for (auto& kw : keyed) h->work_morton.push_back(kw.second);
+  }
   h->sum_normflux = 0.0;
   for (int s = 0; s < NumSrc; ++s) h->sum_normflux = h->sum_normflux + nf[s];  // sum(NormFlux_stellar(1:NumSrc))
   if (NumSrc == 0) return 0;
@@ -774,7 +798,8 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     // whole list is short.
     std::vector<int> small, large;
     const bool few = (int)h->work.size() <= h->cluster_max_sources;
-    for (int w : h->work) {
+    const bool zorder = !(getenv("C2B_NO_ZORDER") && atoi(getenv("C2B_NO_ZORDER")));
+    for (int w : (zorder ? h->work_morton : h->work)) {
       const int pred = h->nbox_pred[w];
       const bool is_large = pred >= h->cluster_min_nbox || (pred == 0 && few && h->cluster_min_nbox < 100000);
       (is_large ? large : small).push_back(w);

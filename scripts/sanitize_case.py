@@ -1,0 +1,15 @@
+"""Small evolve3D runs for compute-sanitizer (memcheck / racecheck): both ray-trace kernels, all LLS modes."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from problems import make_problem, setup_gpu
+for mode in ("cta", "cluster"):
+    os.environ["C2B_CLUSTER_MIN_NBOX"] = "100000" if mode == "cta" else "0"
+    os.environ["C2B_CLUSTER_MAX_SOURCES"] = "1000000"
+    for case in (dict(N=24, nsrc=3, seed=5, state="ionized", use_LLS=True),
+                 dict(N=(16, 20, 12), nsrc=2, seed=5, state="ionized", use_LLS=True, type_of_LLS=2, clumping="grid")):
+        p = make_problem(**case)
+        e = setup_gpu(p)
+        rep = e.evolve3D(0.0, 3.15576e13)
+        print(mode, case["N"], "niter", rep.niter, "updates", rep.total_updates, flush=True)
+        e.close()
