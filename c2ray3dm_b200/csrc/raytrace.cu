@@ -18,13 +18,18 @@
 // but only the quadrant the reference's branch order selects "owns" the cell: it alone adds the
 // rate into phih_grid and counts the boundary loss.
 //
-// Mapping.  One CTA per source, persistent CTAs pulling sources from an atomic ticket (the
-// device-side do_grid_master, master_slave.F90:124-231).  Within a shell a thread owns a column
-// (quadrant q, transverse index a) and walks b = 0..r: the two upstream values of its own column
-// stay in registers from one b to the next, the two of column a-1 arrive by warp shuffle, so a cell
-// costs one plane load.  The planes of shell r-1 and r live in shared memory while
-// 24*(r+1)^2 doubles fit, afterwards in a per-CTA global scratch that stays L2 resident.
-// The optical-depth table is staged in shared memory as (value, forward difference) pairs.
+// Mapping.  One work group per source, persistent work groups pulling sources from an atomic ticket
+// (the device-side do_grid_master, master_slave.F90:124-231).  A work group is one CTA of 256 threads
+// (three resident per SM) or, when there are too few long traces to fill the GPU that way, a
+// thread-block cluster of 8 CTAs, one per octant with its three face quadrants, whose boundary-loss
+// partial sums meet in rank 0's shared memory over DSMEM once per subbox pass.  Within a shell a
+// thread owns a column (quadrant q, transverse index a), or a b-segment of it, and walks b: the two
+// upstream values of its own column stay in registers from one b to the next, the two of column a-1
+// arrive by warp shuffle, so a cell costs one plane load, requested one row ahead together with the
+// grid value.  The planes of shell r-1 and r live in shared memory while they fit, afterwards in a
+// per-CTA global scratch.  The optical-depth table is staged in shared memory as (value, forward
+// difference) pairs.  Quadrants whose principal axis is x walk planes of constant x; they read and
+// accumulate into y-fastest twins of the grids so that their accesses are contiguous too.
 //
 // Arithmetic.  The planes hold optical depths tau = sigma_HI * N_HI; the per-cell opacity
 // tau_cell = sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens comes from a grid the per-cell kernel
@@ -504,17 +509,12 @@ struct ClusterVariant {
   int ctas_per_sm() const { return threads <= 256 ? 2 : 1; }
 };
 static const ClusterVariant kVariants[] = {
-    {512, 8, 1, pick_kernel<512, 8, 1>},  // 0: one octant per CTA, one barrier domain
-    {480, 8, 3, pick_kernel<480, 8, 3>},  // 1: one octant per CTA, one warp group per face quadrant
-    {512, 4, 2, pick_kernel<512, 4, 2>},  // 2: two octants per CTA, one group per octant
-    {512, 4, 1, pick_kernel<512, 4, 1>},  // 3
-    {512, 2, 2, pick_kernel<512, 2, 2>},  // 4: four octants per CTA, two groups
-    {576, 4, 6, pick_kernel<576, 4, 6>},  // 5: two octants per CTA, one group per face quadrant
-    {256, 8, 1, pick_kernel<256, 8, 1>},  // 6: one octant per CTA, two CTAs (two sources) per SM
-    {256, 4, 1, pick_kernel<256, 4, 1>},  // 7: two octants per CTA, two CTAs per SM
-    {256, 2, 1, pick_kernel<256, 2, 1>},  // 8: four octants per CTA, two CTAs per SM
+    {512, 8, 1, pick_kernel<512, 8, 1>},  // 0: one octant per CTA, one CTA per SM (planes in shared memory up to r = 63)
+    {480, 8, 3, pick_kernel<480, 8, 3>},  // 1: as 0 with one warp group (own named barrier) per face quadrant
+    {256, 8, 1, pick_kernel<256, 8, 1>},  // 2: one octant per CTA, two CTAs (two sources) per SM  [default]
+    {256, 2, 1, pick_kernel<256, 2, 1>},  // 3: four octants per CTA, two CTAs per SM
 };
-static int g_variant = 6;
+static int g_variant = 2;
 
 static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, const ClusterVariant& v, int nclusters,
                            size_t smem, cudaStream_t stream) {

@@ -477,3 +477,29 @@ def test_full_box_trace_spills_planes_to_global(gpu_tables):
     assert g.updates == 100 ** 3 and g.sum_nbox_all == 10
     _rates_close(e.phih_grid, o.phih)
     e.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_cluster_kernel_shapes(variant, gpu_tables, monkeypatch):
+    """every compiled shape of the cluster kernel (octant per CTA with one or three warp groups, one or
+    two CTAs per SM, four octants per CTA) gives the oracle's answer"""
+    monkeypatch.setenv("C2B_CLUSTER_VARIANT", str(variant))
+    monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "0")
+    monkeypatch.setenv("C2B_CLUSTER_MAX_SOURCES", "1000000")
+    monkeypatch.setenv("C2B_DEBUG_CLUSTER", "1")
+    p = _problem(dict(N=40, nsrc=5, seed=31, state="random", use_LLS=True))
+    e = setup_gpu(p, tables=gpu_tables)
+    o = setup_oracle(p, tables=gpu_tables)
+    ro = o.evolve3D(DT)
+    rg = e.evolve3D(0.0, DT)
+    assert rg.niter == ro.niter and rg.total_updates == ro.total_updates
+    np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+    _rates_close(e.phih_grid, o.phih)
+    cd, ph, nbox, loss = e.trace_source_debug(2)
+    o2 = setup_oracle(p, tables=gpu_tables)
+    o2.xh_av[...] = e.xh_av
+    o2.set_rates_to_zero()
+    rr = o2.do_source(2)
+    assert nbox == rr.nbox
+    np.testing.assert_allclose(cd, o2.coldensh_out, rtol=1e-11, atol=0)
+    e.close()
