@@ -13,8 +13,11 @@ DT = 1e6 * 3.15576e7
 
 
 def _ngpu():
-    from c2ray3dm_b200 import lib
-    return lib.load().c2b_device_count()
+    try:
+        from c2ray3dm_b200 import lib
+        return lib.load().c2b_device_count()
+    except Exception:
+        return 0
 
 
 def _worker(rank, world, uid, q, case):
