@@ -1,0 +1,248 @@
+// module evolve, C++ edition: the outer multi-source convergence loop of evolve.F90:83-281 with its log
+// lines, driving the device through the fine-grained C ABI.  Mirrors fortran/evolve_b200.F90 statement by
+// statement.
+#include "c2ray_host.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <iomanip>
+#include <iostream>
+
+#include "../include/c2ray_b200.h"
+
+namespace c2ray {
+
+namespace sizes { int mesh[3] = {0, 0, 0}; }
+namespace my_mpi { int rank = 0, npr = 1; }
+namespace file_admin { std::ostream* logf = &std::cout; std::ostream* timefile = nullptr; }
+namespace grid { double dr[3] = {0, 0, 0}, vol = 0; }
+namespace density_module { std::vector<float> ndens; }
+namespace ionfractions_module { std::vector<double> xh; }
+namespace temperature_module { double temper_val = 1e4; }
+namespace clumping_module { float clumping = 1.0f; std::vector<float> clumping_grid; }
+namespace LLS_module { double coldensh_LLS = 0, R_max_LLS = 0; std::vector<float> LLS_grid; }
+namespace sourceprops { int NumSrc = 0; std::vector<int32_t> srcpos; std::vector<double> NormFlux_stellar; }
+namespace radiation_sed_parameters { double S_star = 1e48; }
+namespace radiation_tables { std::vector<double> stellar_photo_thick_table, stellar_photo_thin_table; }
+namespace c2ray_parameters {
+int type_of_clumping = 1, type_of_LLS = 1;
+bool use_LLS = true, isothermal = true;
+double convergence_fraction = (double)1.0e-4f;
+}
+namespace evolve_data { std::vector<double> phih_grid, xh_av, xh_intermed; double photon_loss_all[1] = {0}; }
+namespace evolve_source { int sum_nbox_all = 0; }
+namespace photonstatistics {
+double totrec = 0, totcollisions = 0, dh0 = 0, total_ion = 0, LLS_loss = 0, grtotal_ion = 0, grtotal_src = 0,
+       photon_loss[1] = {0};
+}
+
+namespace evolve {
+
+namespace {
+c2b_handle* handle = nullptr;
+std::string g_error;
+bool g_ok = true;
+int g_niter = 0;
+double prev_sum_xh1_int, prev_sum_xh0_int, rel_change_sum_xh1, rel_change_sum_xh0;
+
+bool check(int rc, const char* what) {
+  if (rc == 0) return true;
+  g_ok = false;
+  g_error = std::string(what) + ": " + c2b_last_error(handle);
+  if (my_mpi::rank == 0 && file_admin::logf) *file_admin::logf << "c2ray_b200 error: " << g_error << "\n";
+  return false;
+}
+
+// creates the device handle on first use (evolve_ini, evolve_data.F90:73-93)
+bool b200_init() {
+  c2b_config cfg;
+  c2b_default_config(&cfg);
+  for (int d = 0; d < 3; ++d) cfg.mesh[d] = sizes::mesh[d];
+  cfg.rank = my_mpi::rank;
+  cfg.nranks = my_mpi::npr;
+  cfg.device = my_mpi::rank % 8;
+  cfg.type_of_clumping = c2ray_parameters::type_of_clumping;
+  cfg.use_LLS = c2ray_parameters::use_LLS ? 1 : 0;
+  cfg.type_of_LLS = c2ray_parameters::type_of_LLS;
+  cfg.isothermal = c2ray_parameters::isothermal ? 1 : 0;
+  cfg.convergence_fraction = c2ray_parameters::convergence_fraction;
+  const int rc = c2b_create(&cfg, &handle);
+  if (rc != 0) {
+    g_ok = false;
+    g_error = std::string("c2b_create: ") + c2b_last_error(nullptr);
+    if (file_admin::logf) *file_admin::logf << "c2ray_b200 error: " << g_error << "\n";
+    handle = nullptr;
+    return false;
+  }
+  // rad_ini has already run on the host (radiation_tables.F90:95): hand over its tables
+  return check(c2b_set_tables(handle, radiation_tables::stellar_photo_thick_table.data(),
+                              radiation_tables::stellar_photo_thin_table.data(),
+                              (int32_t)radiation_tables::stellar_photo_thick_table.size()),
+               "c2b_set_tables");
+}
+
+// the module state evolve3D reads (SURVEY 8b "hidden inputs")
+bool b200_upload_state() {
+  using namespace c2ray_parameters;
+  if (!check(c2b_set_density(handle, density_module::ndens.data()), "c2b_set_density")) return false;
+  if (!check(c2b_set_geometry(handle, grid::dr, grid::vol), "c2b_set_geometry")) return false;
+  if (!check(c2b_set_temperature(handle, temperature_module::temper_val), "c2b_set_temperature")) return false;
+  if (type_of_clumping >= 3) {
+    if (!check(c2b_set_clumping_grid(handle, clumping_module::clumping_grid.data()), "c2b_set_clumping_grid")) return false;
+  } else if (!check(c2b_set_clumping_scalar(handle, clumping_module::clumping), "c2b_set_clumping_scalar")) {
+    return false;
+  }
+  if (use_LLS) {
+    int rc = 0;
+    if (type_of_LLS == 1) rc = c2b_set_lls_scalar(handle, LLS_module::coldensh_LLS);
+    else if (type_of_LLS == 2) rc = c2b_set_lls_grid(handle, LLS_module::LLS_grid.data());
+    else rc = c2b_set_lls_rmax(handle, LLS_module::R_max_LLS);
+    if (!check(rc, "c2b_set_lls")) return false;
+  }
+  if (!check(c2b_set_sources(handle, sourceprops::NumSrc, sourceprops::srcpos.data(),
+                             sourceprops::NormFlux_stellar.data(), radiation_sed_parameters::S_star),
+             "c2b_set_sources"))
+    return false;
+  return check(c2b_set_xh(handle, ionfractions_module::xh.data()), "c2b_set_xh");
+}
+
+void absorb_stats(const c2b_photon_stats& s) {
+  using namespace photonstatistics;
+  totrec = s.totrec;
+  totcollisions = s.totcollisions;
+  dh0 = s.dh0;
+  total_ion = s.total_ion;
+  LLS_loss = s.LLS_loss;
+  photon_loss[0] = evolve_data::photon_loss_all[0] /
+                   (double)((float)sizes::mesh[0] * (float)sizes::mesh[1] * (float)sizes::mesh[2]);
+}
+
+// report_photonstatistics, photonstatistics.F90:254-281
+void report_stats(const c2b_photon_stats& s) {
+  if (my_mpi::rank != 0 || !file_admin::logf) return;
+  std::ostream& o = *file_admin::logf;
+  o << std::scientific << std::setprecision(3) << s.total_ion << " " << s.totalsrc << " " << s.photcons << " "
+    << s.dh0 / s.total_ion << " " << s.totrec / s.total_ion << " " << s.LLS_loss / s.totalsrc << " "
+    << s.total_photon_loss / s.totalsrc << " " << s.totcollisions / s.total_ion << "\n";
+  o << std::setprecision(16) << s.h1_before << " " << s.h1_after << "\n";
+}
+
+}  // namespace
+
+bool ok() { return g_ok; }
+const std::string& last_error() { return g_error; }
+int last_niter() { return g_niter; }
+void shutdown() {
+  if (handle) c2b_destroy(handle);
+  handle = nullptr;
+}
+
+void evolve3D(double time, double dt, int restart) {
+  (void)time;
+  using sizes::mesh;
+  const bool root = my_mpi::rank == 0 && file_admin::logf;
+  std::ostream& logf = file_admin::logf ? *file_admin::logf : std::cout;
+  g_ok = true;
+  if (!handle && !b200_init()) return;
+  if (!b200_upload_state()) return;
+
+  int niter = 0;
+  int conv_flag = 0;
+  double sum_xh1_int = 0.0;
+  if (restart == 0) {
+    // state_before ; xh_av=xh ; xh_intermed=xh  (evolve.F90:136-147)
+    if (!check(c2b_begin_step(handle, &sum_xh1_int), "c2b_begin_step")) return;
+    niter = 0;
+    conv_flag = mesh[0] * mesh[1] * mesh[2];
+    prev_sum_xh1_int = (double)(2.0f * (float)mesh[0] * (float)mesh[1] * (float)mesh[2]);
+    prev_sum_xh0_int = prev_sum_xh1_int;
+    rel_change_sum_xh1 = 1.0;
+    rel_change_sum_xh0 = 1.0;
+  } else {
+    // start_from_dump (evolve.F90:328-426): the caller has filled phih_grid, xh_av, xh_intermed,
+    // photon_loss_all from iterdump[12].bin and passes the dumped niter as `restart`
+    c2b_global_report gr;
+    if (!check(c2b_begin_step(handle, &sum_xh1_int), "c2b_begin_step")) return;
+    if (!check(c2b_set_iter_state(handle, restart, evolve_data::photon_loss_all[0], evolve_data::phih_grid.data(),
+                                  evolve_data::xh_av.data(), evolve_data::xh_intermed.data()),
+               "c2b_set_iter_state"))
+      return;
+    if (!check(c2b_global_pass(handle, dt, &gr), "c2b_global_pass")) return;
+    niter = restart;
+    conv_flag = gr.conv_flag;
+    sum_xh1_int = gr.sum_xh_intermed;
+  }
+  const int conv_criterion =
+      std::min((int)(c2ray_parameters::convergence_fraction * mesh[0] * mesh[1] * mesh[2]), (sourceprops::NumSrc - 1) / 3);
+
+  int32_t converged = 0;
+  for (;;) {
+    const double sum_xh0_int = (double)(float)(mesh[0] * mesh[1] * mesh[2]) - sum_xh1_int;   // evolve.F90:183-196
+    rel_change_sum_xh1 = (sum_xh1_int > 0.0) ? std::fabs(sum_xh1_int - prev_sum_xh1_int) / sum_xh1_int : 1.0;
+    rel_change_sum_xh0 = (sum_xh0_int > 0.0) ? std::fabs(sum_xh0_int - prev_sum_xh0_int) / sum_xh0_int : 1.0;
+    if (root) {
+      logf << "Convergence tests: \n";
+      logf << "   Test 1 values: " << conv_flag << " " << conv_criterion << "\n";
+      logf << "   Test 2 values: " << rel_change_sum_xh1 << " " << rel_change_sum_xh0 << " "
+           << c2ray_parameters::convergence_fraction << "\n";
+    }
+    if (conv_flag < conv_criterion || (rel_change_sum_xh1 < c2ray_parameters::convergence_fraction &&
+                                       rel_change_sum_xh0 < c2ray_parameters::convergence_fraction)) {
+      converged = 1;
+      if (root) logf << "Multiple sources convergence reached\n";
+      break;
+    } else if (niter > 100) {
+      if (root) logf << "Multiple sources not converging\n";
+      break;
+    }
+    prev_sum_xh1_int = sum_xh1_int;
+    prev_sum_xh0_int = sum_xh0_int;
+    niter = niter + 1;
+
+    // set_rates_to_zero + pass_all_sources (+ the all-reduces of evolve.F90:577-616)
+    if (root) logf << "Doing all sources \n";
+    c2b_pass_report pr;
+    if (!check(c2b_pass_all_sources(handle, niter, dt, &pr), "c2b_pass_all_sources")) return;
+    evolve_data::photon_loss_all[0] = pr.photon_loss_all;
+    evolve_source::sum_nbox_all = (int)pr.sum_nbox_all;
+    if (root)
+      logf << "Average number of subboxes: " << (float)evolve_source::sum_nbox_all / (float)sourceprops::NumSrc << "\n";
+
+    // global_pass (evolve.F90:499-573)
+    c2b_global_report gr;
+    if (!check(c2b_global_pass(handle, dt, &gr), "c2b_global_pass")) return;
+    conv_flag = gr.conv_flag;
+    sum_xh1_int = gr.sum_xh_intermed;
+    if (root) {
+      logf << "min value avg neutral fraction: " << gr.min_avg_neutral << "\n";
+      logf << "Doing global \n";
+      logf << "Number of non-converged points: " << conv_flag << "\n";
+      logf << "Intermediate result for mean H ionization fraction: "
+           << sum_xh1_int / (double)(float)(mesh[0] * mesh[1] * mesh[2]) << "\n";
+    }
+    absorb_stats(gr.stats);
+    report_stats(gr.stats);
+  }
+  g_niter = niter;
+
+  // xh=xh_intermed if converged ; calculate_photon_statistics(dt,xh,xh_av) ; grand totals (evolve.F90:215-279)
+  c2b_photon_stats stats;
+  if (!check(c2b_end_step(handle, dt, converged, &stats), "c2b_end_step")) return;
+  absorb_stats(stats);
+  report_stats(stats);
+  photonstatistics::grtotal_src += stats.totalsrc;
+  photonstatistics::grtotal_ion += photonstatistics::total_ion - photonstatistics::totcollisions;
+
+  // host copies for output.F90 (streams 2 and 3) and for the next call
+  const size_t n = (size_t)mesh[0] * mesh[1] * mesh[2];
+  evolve_data::phih_grid.resize(n);
+  evolve_data::xh_av.resize(n);
+  evolve_data::xh_intermed.resize(n);
+  if (!check(c2b_get_xh(handle, ionfractions_module::xh.data()), "c2b_get_xh")) return;
+  if (!check(c2b_get_phih(handle, evolve_data::phih_grid.data()), "c2b_get_phih")) return;
+  if (!check(c2b_get_xh_av(handle, evolve_data::xh_av.data()), "c2b_get_xh_av")) return;
+  check(c2b_get_xh_intermed(handle, evolve_data::xh_intermed.data()), "c2b_get_xh_intermed");
+}
+
+}  // namespace evolve
+}  // namespace c2ray

@@ -13,7 +13,8 @@ def pytest_configure(config):
     # the built libraries are git-ignored: build them on a fresh checkout (nvcc cross-compiles without a GPU)
     lib = os.path.join(ROOT, "c2ray3dm_b200", "libc2ray_b200.so")
     orc = os.path.join(ROOT, "oracle", "libc2ray_oracle.so")
-    if not (os.path.exists(lib) and os.path.exists(orc)):
+    drv = os.path.join(ROOT, "host", "run_case")
+    if not (os.path.exists(lib) and os.path.exists(orc) and os.path.exists(drv)):
         import __graft_entry__
         __graft_entry__.build()
 
