@@ -216,6 +216,10 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
       g_create_error = "c2b_create: mesh must be within [4, 4096] per axis";
       return 101;
     }
+  if ((double)cfg->mesh[0] * (double)cfg->mesh[1] * (double)cfg->mesh[2] >= 4294967296.0) {
+    g_create_error = "c2b_create: mesh(1)*mesh(2)*mesh(3) must be below 2^32 (cell indices are 32-bit on the device)";
+    return 101;
+  }
   if (!cfg->isothermal) {
     g_create_error = "c2b_create: only isothermal=.true. is implemented (thermal.f90 needs tables/corocool.tab, absent from the reference)";
     return 102;
