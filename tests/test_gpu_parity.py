@@ -328,16 +328,19 @@ def test_phih_single_precision_output(gpu_tables):
 
 
 # ---- properties at sizes the oracle cannot reach ---------------------------------------------------
-def test_linearity_in_sources_at_128(gpu_tables):
-    """rates are additive over sources at fixed xh_av (evolve_point.F90:283): trace A, B and A+B on 128^3"""
+@pytest.mark.parametrize("N,nsrc,bubble", [(128, 40, 9.0), (256, 60, 14.0)], ids=["128", "256_bench_mesh"])
+def test_linearity_in_sources(N, nsrc, bubble, gpu_tables):
+    """rates are additive over sources at fixed xh_av (evolve_point.F90:283): trace A, B and A+B on the
+    benchmark's kind of inputs (log-normal density, sources at the peaks, bubble state, LLS), including the
+    benchmark's mesh size, where the oracle is out of reach"""
     from c2ray3dm_b200 import synthetic as syn
-    N = 128
     nd = syn.lognormal_density(N, 9.0, 77)
-    pos, nf = syn.sources_at_density_peaks(nd, 40, 3e8)
-    xh = syn.bubble_state(nd.shape, pos, 9.0)
+    pos, nf = syn.sources_at_density_peaks(nd, nsrc, 3e8)
+    xh = syn.bubble_state(nd.shape, pos, bubble)
     dr, vol = syn.proper_geometry(N, 9.0)
+    half = nsrc // 2
     out = []
-    for sel in (slice(0, 20), slice(20, 40), slice(0, 40)):
+    for sel in (slice(0, half), slice(half, nsrc), slice(0, nsrc)):
         e = __import__("c2ray3dm_b200").Evolve(N, use_LLS=True)
         e.set_tables(*gpu_tables)
         e.set_density(nd)
@@ -347,11 +350,13 @@ def test_linearity_in_sources_at_128(gpu_tables):
         e.set_xh(xh)
         e.begin_step()
         r = e.pass_all_sources()
-        out.append((e.phih_grid, r))
+        out.append((e.phih_grid, r, e.source_nbox()))
         e.close()
     np.testing.assert_allclose(out[0][0] + out[1][0], out[2][0], rtol=1e-10, atol=1e-30)
     assert out[0][1].updates + out[1][1].updates == out[2][1].updates
     assert out[0][1].photon_loss_all + out[1][1].photon_loss_all == pytest.approx(out[2][1].photon_loss_all, rel=1e-10)
+    assert list(out[0][2]) + list(out[1][2]) == list(out[2][2])       # per-source subbox counts are independent
+    assert out[2][1].updates > 20 * nsrc * 1331                        # the traces do leave the first subbox
 
 
 def test_translation_invariance_periodic(gpu_tables):
