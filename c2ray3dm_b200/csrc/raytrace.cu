@@ -35,9 +35,10 @@
 // tau_cell = sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens comes from a grid the per-cell kernel
 // writes, so an update reads 8 bytes and adds 8.  The reference's five divisions per interpolation
 // collapse into one (common denominator), the two log10 of the table look-up become a 128-entry
-// table + degree-5 polynomial log2 folded into the table coordinate, path and 1/vol_ph come from
-// one reciprocal square root.  All of it stays within ~1e-13 of the CPU restatement (tests bound
-// the rates at 1e-6 relative as BASELINE.json requires).
+// table + degree-5 polynomial log2 folded into the table coordinate, the path length comes from a
+// reciprocal square root, and the reciprocals are hardware seeds with one third-order refinement.
+// All of it stays within ~1e-13 of the CPU restatement (tests bound the rates at 1e-6 relative as
+// BASELINE.json requires).
 #include <cooperative_groups.h>
 
 #include <algorithm>
