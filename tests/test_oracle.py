@@ -285,3 +285,35 @@ def test_source_parallel_threads_match_serial():
         outs.append((o.phih.copy(), r))
     np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-12, atol=0)
     assert outs[0][1].updates == outs[1][1].updates and outs[0][1].sum_nbox_all == outs[1][1].sum_nbox_all
+
+
+def _box_updates(mesh, nbox, subboxsize=5, max_subbox=1000):
+    """closed form the product uses to count updates from a source's final nbox (SURVEY A2b;
+    c2b_api.cu: box_updates): cells of [-min(5n,L), +min(5n,R)] per axis"""
+    if nbox <= 0:
+        return 0
+    u = 1
+    for m in mesh:
+        R = min(max_subbox, m // 2 - 1 + m % 2)
+        L = min(max_subbox, m // 2)
+        u *= min(subboxsize * nbox, R) + min(subboxsize * nbox, L) + 1
+    return u
+
+
+@pytest.mark.parametrize("mesh", [(10, 10, 10), (12, 12, 12), (21, 21, 21), (22, 22, 22), (16, 20, 12), (24, 14, 30), (31, 18, 18)])
+def test_update_count_closed_form(mesh):
+    """the number of evolve0D calls passing the gate equals the volume of the final subbox, for every subbox
+    count a trace can end with (forced here through the loss threshold), cubic and non-cubic meshes"""
+    p = make_problem(mesh, nsrc=1, seed=9, state="ionized", use_LLS=True, flux=1e10)
+    seen = set()
+    for lf in (0.0, 1e-6, 1e-3, 3e-2, 0.2, 0.6, 0.9, 0.999):
+        o = setup_oracle(p)
+        o.set_loss_fraction(lf)
+        o.xh_av[...] = p["xh"]
+        o.set_rates_to_zero()
+        r = o.do_source(1)
+        assert r.updates == _box_updates(mesh, r.nbox)
+        assert int(np.count_nonzero(o.coldensh_out)) == r.updates
+        seen.add(r.nbox)
+    if min(mesh) > 12:
+        assert len(seen) >= 2
