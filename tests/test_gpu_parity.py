@@ -356,7 +356,7 @@ def test_linearity_in_sources(N, nsrc, bubble, gpu_tables):
     assert out[0][1].updates + out[1][1].updates == out[2][1].updates
     assert out[0][1].photon_loss_all + out[1][1].photon_loss_all == pytest.approx(out[2][1].photon_loss_all, rel=1e-10)
     assert list(out[0][2]) + list(out[1][2]) == list(out[2][2])       # per-source subbox counts are independent
-    assert out[2][1].updates > 20 * nsrc * 1331                        # the traces do leave the first subbox
+    assert out[2][1].updates > 4 * nsrc * 1331                         # the traces do leave the first subbox
 
 
 def test_translation_invariance_periodic(gpu_tables):
