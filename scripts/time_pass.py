@@ -1,4 +1,5 @@
-"""Timing study: one pass_all_sources on a fixed state with parts of the update switched off (C2B_ABLATE)."""
+"""Timing study: repeated pass_all_sources on a fixed mid-reionization state (no chemistry in between), so
+kernel changes can be compared on identical work:  python scripts/time_pass.py [mesh] [nsrc]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,7 +14,6 @@ e.rad_ini(); e.set_geometry(w["dr"], w["vol"]); e.set_clumping(w["clumping"]); e
 e.set_sources(w["srcpos"], w["normflux"]); e.set_density(w["ndens"]); e.set_xh(w["xh"])
 e.evolve3D(0.0, 0.5e6 * 3.15576e7)
 e.begin_step()
-for ab in (0, 0, 1, 2, 3):
-    os.environ["C2B_ABLATE"] = str(ab)
+for rep in range(3):
     r = e.pass_all_sources()
-    print("ablate %d: %.1f ms, %.2f G updates/s (%d updates)" % (ab, r.ms_raytrace, r.updates / r.ms_raytrace / 1e6, r.updates), flush=True)
+    print("pass %d: %.1f ms, %.2f G updates/s (%d updates)" % (rep, r.ms_raytrace, r.updates / r.ms_raytrace / 1e6, r.updates), flush=True)
