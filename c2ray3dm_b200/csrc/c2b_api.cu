@@ -683,6 +683,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.S_star = h->S_star;
   rp.vol = h->vol;
   rp.use_lls = c.use_LLS;
+  rp.cubic_cells = (h->dr[0] == h->dr[1] && h->dr[1] == h->dr[2]) ? 1 : 0;
   rp.type_lls = c.type_of_LLS;
   rp.tau_lls = c.sigma_HI * h->coldensh_LLS;
   rp.rmax_lls2 = h->R_max_LLS * h->R_max_LLS;

@@ -50,6 +50,7 @@ struct RtParams {
   double tau_stop;          // sigma_HI*max_coldensh (evolve_point.F90:95,201)
   double vol_cell;          // dr(1)*dr(2)*dr(3), vol_ph of the source cell (:153)
   int use_lls, type_lls;
+  int cubic_cells;          // dr(1)==dr(2)==dr(3)
   double tau_lls;           // sigma_HI*coldensh_LLS
   double rmax_lls2;
   double sigma_HI, inv_sigma, inv_sigma_dr0, fourpi_over_sigma;

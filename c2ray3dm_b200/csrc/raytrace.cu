@@ -141,6 +141,17 @@ __device__ __forceinline__ void photo_rates(double tau_in, double tau_out, doubl
   }
 }
 
+// dist2 = xs*xs+ys*ys+zs*zs of evolve_point.F90:170-174 for the cell (principal offset r, transverse a, b).
+// Cubic cells (the reference's grids: dr(1)=dr(2)=dr(3)) need only dr^2 * (r^2+a^2+b^2) = dr^2 * q2; the general
+// form is evaluated on demand so that no per-axis factors stay live in the row loop.
+__device__ __forceinline__ double dist2_of(const RtParams& P, int p, int r, int a, double b2, double q2) {
+  if (P.cubic_cells) return P.dr2[0] * q2;
+  const double dP = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
+  const double dA = (p == 2) ? P.dr2[1] : P.dr2[0];
+  const double dB = (p == 0) ? P.dr2[1] : P.dr2[2];
+  return fma(dB, b2, fma(dP, (double)(r * r), dA * (double)(a * a)));
+}
+
 __device__ __forceinline__ int wrap(int x, int n) {
   // modulo(x-1,mesh)+1 of evolve_point.F90:122-124 for |offset| <= n/2, 0-based
   if (x < 0) x += n;
@@ -293,9 +304,6 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
           const unsigned strideB = (p == 0) ? st1 : (p == 1 ? st2 : (unsigned)n1);
           const double* __restrict__ g_tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
           double* __restrict__ g_phih = (p == 2) ? P.phih_t : P.phih;
-          const double dr2P = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
-          const double dr2A = (p == 2) ? P.dr2[1] : P.dr2[0];
-          const double dr2B = (p == 0) ? P.dr2[1] : P.dr2[2];
           const unsigned base = (unsigned)wrap(srcP + sp * r, nP) * strP + (unsigned)wrap(srcA + sa * a, nA) * strA;
           int posB = srcB + sb * b0;
           if (posB < 0) posB += nB;
@@ -305,7 +313,6 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
           // column-level geometry
           const double ua = (double)a * inv_r;   // 1-dx of cinterp (a==r gives 1 to an ulp; the cells it would exclude read as 0)
           const double ca2 = (double)(r * r + a * a);
-          const double dist_col = dr2P * (double)(r * r) + dr2A * (double)(a * a);
           // ownership pieces that do not depend on b (see header comment)
           const bool own_col = (a > 0 || sa > 0) && (p != 2 || a < r);
           // owned rows of this column: b in [own_lo, own_hi] (b==0 belongs to the sb>0 quadrant; b==r belongs
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
               const double rs = fast_rsqrt(q2);
               const double pathc = q2 * rs * inv_r;                        // sqrt(1+(a^2+b^2)/r^2)
               if (kLls == 3) {  // evolve_point.F90:186-196
-                if (fma(dr2B, b2, dist_col) > P.rmax_lls2) stop = true;
+                if (dist2_of(P, p, r, a, b2, q2) > P.rmax_lls2) stop = true;
               } else if (kLls == 2) {
                 tau_in = fma((double)P.lls_grid[(p == 2) ? xcell : cell] * P.sigma_HI, pathc, tau_in);
               } else if (kLls == 1) {
@@ -402,7 +409,7 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
                   double phi_all, phi_out;
                   photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
                   // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI) = phi_all/volfac
-                  const double dist2 = fma(dr2B, b2, dist_col);
+                  const double dist2 = dist2_of(P, p, r, a, b2, q2);
                   const double volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
                   const double inv_vol = fast_rcp(volfac);
                   const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262

@@ -508,3 +508,20 @@ def test_cluster_kernel_shapes(variant, gpu_tables, monkeypatch):
     assert nbox == rr.nbox
     np.testing.assert_allclose(cd, o2.coldensh_out, rtol=1e-11, atol=0)
     e.close()
+
+
+def test_non_cubic_cells(gpu_tables):
+    """dr(1) != dr(2) != dr(3): dist2 uses the three cell sizes, the path length only dr(1)
+    (evolve_point.F90:166-177); the kernel takes its general-dist2 branch"""
+    p = _problem(dict(N=(20, 24, 16), nsrc=4, seed=51, state="random", use_LLS=True))
+    p["dr"] = p["dr"] * np.array([1.0, 1.3, 0.8])
+    p["vol"] = float(np.prod(p["dr"]))
+    e = setup_gpu(p, tables=gpu_tables)
+    o = setup_oracle(p, tables=gpu_tables)
+    ro = o.evolve3D(DT)
+    rg = e.evolve3D(0.0, DT)
+    assert rg.niter == ro.niter and rg.total_updates == ro.total_updates
+    np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+    _rates_close(e.phih_grid, o.phih)
+    assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
+    e.close()
