@@ -317,3 +317,62 @@ def test_update_count_closed_form(mesh):
         seen.add(r.nbox)
     if min(mesh) > 12:
         assert len(seen) >= 2
+
+
+def test_upstream_cells_outside_previous_shell_have_zero_weight():
+    """SURVEY A3, the fact the GPU wavefront rests on: the upstream cells cinterp reads that are NOT in the
+    previous Chebyshev shell (same-shell cells on cube edges/diagonals, the i-1 neighbour of an on-axis cell)
+    carry a bilinear weight of exactly 0.  Checked by poisoning every cell outside shell r-1 with 1e300: the
+    interpolated column density must not change by a single bit.  Radii up to 99, sources near a corner so
+    that the periodic wrap is exercised."""
+    N = 200
+    rng = np.random.default_rng(5)
+    zero = O.Oracle(N)
+    pois = O.Oracle(N)
+    pois.coldensh_out[...] = 1e300
+    cz, cp = zero.coldensh_out, pois.coldensh_out
+    checked = 0
+    for src in ((3, 198, 100), (100, 100, 100), (200, 1, 2)):
+        s = np.array(src)
+        for r in list(range(1, 12)) + [17, 25, 40, 64, 77, 99]:
+            # cells of shell r: corners, edges, face centres (on-axis), near-diagonals and random ones
+            cells = set()
+            for sg in ((1, 1, 1), (-1, 1, -1), (1, -1, -1), (-1, -1, 1)):
+                cells.add((sg[0] * r, sg[1] * r, sg[2] * r))
+                cells.add((sg[0] * r, sg[1] * r, 0))
+                cells.add((sg[0] * r, 0, sg[2] * r))
+                cells.add((0, sg[1] * r, sg[2] * r))
+                cells.add((sg[0] * r, 0, 0))
+                cells.add((0, sg[1] * r, 0))
+                cells.add((0, 0, sg[2] * r))
+                cells.add((sg[0] * r, sg[1] * (r - 1), sg[2] * 1))
+                cells.add((sg[0] * 1, sg[1] * r, sg[2] * (r - 1)))
+            for _ in range(12):
+                d = rng.integers(-r, r + 1, size=3)
+                d[rng.integers(0, 3)] = r * rng.choice((-1, 1))
+                cells.add(tuple(int(v) for v in d))
+            for d in cells:
+                pos = s + np.array(d)
+                # the (up to) four upstream cells, one step closer to the source along every axis
+                sg = [1 if v >= 0 else -1 for v in d]
+                ups = set()
+                for ox in (0, 1):
+                    for oy in (0, 1):
+                        for oz in (0, 1):
+                            ups.add((d[0] - ox * sg[0], d[1] - oy * sg[1], d[2] - oz * sg[2]))
+                touched = []
+                for u in ups:
+                    if max(abs(u[0]), abs(u[1]), abs(u[2])) == r - 1:      # in the previous shell: a real value
+                        q = (s + np.array(u) - 1) % N
+                        v = float(rng.uniform(1e16, 3e19))
+                        cz[q[2], q[1], q[0]] = v
+                        cp[q[2], q[1], q[0]] = v
+                        touched.append(q)
+                a = zero.cinterp(pos, s)
+                b = pois.cinterp(pos, s)
+                assert a == b, (src, d)
+                for q in touched:
+                    cz[q[2], q[1], q[0]] = 0.0
+                    cp[q[2], q[1], q[0]] = 1e300
+                checked += 1
+    assert checked > 1500
