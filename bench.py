@@ -36,7 +36,7 @@ UNIT = "updates/s"
 B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 + xh_av 8 + phih RMW 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one raytrace_kernel launch on this workload divided by
 # the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r1_summary.txt)
-NCU_DRAM_BYTES_PER_UPDATE = 28.8
+NCU_DRAM_BYTES_PER_UPDATE = 21.6
 FP64_INSTR_PER_UPDATE = 91  # FP64-pipe instructions in the inner loop of raytrace_kernel (static SASS, scripts/sass_loop.py)
 YEAR = 3.15576e7
 
