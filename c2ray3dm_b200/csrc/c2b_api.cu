@@ -309,6 +309,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   }
   const size_t scratch = raytrace_scratch_doubles_per_cta(h->plane_stride) * (size_t)h->rt_grid;
   if ((e = cudaMalloc(&h->d_scratch, scratch * sizeof(double))) != cudaSuccess) return bail("cudaMalloc scratch", e);
+  // the ray tracer reads zero-weight neighbours outside the planes: they must be finite (raytrace.cu)
+  if ((e = cudaMemsetAsync(h->d_scratch, 0, scratch * sizeof(double), h->stream)) != cudaSuccess) return bail("memset scratch", e);
   h->chem_blocks = chemistry_blocks();
   if ((e = cudaMalloc(&h->d_partials, (size_t)h->chem_blocks * kNumStat * sizeof(double))) != cudaSuccess)
     return bail("cudaMalloc", e);
@@ -685,7 +687,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.use_lls = c.use_LLS;
   rp.cubic_cells = (h->dr[0] == h->dr[1] && h->dr[1] == h->dr[2]) ? 1 : 0;
   rp.type_lls = c.type_of_LLS;
-  rp.tau_lls = c.sigma_HI * h->coldensh_LLS;
+  rp.tau_lls = (c.use_LLS && c.type_of_LLS == 1) ? c.sigma_HI * h->coldensh_LLS : 0.0;  // no LLS == a zero LLS column
   rp.rmax_lls2 = h->R_max_LLS * h->R_max_LLS;
   rp.sigma_HI = c.sigma_HI;
   rp.inv_sigma = 1.0 / c.sigma_HI;

@@ -15,15 +15,16 @@ constexpr int kTableLen = kNumTau + 1;
 
 // ---- ray tracer ------------------------------------------------------------------------------
 // One work item = one source.  A source is traced shell by shell (Chebyshev distance r from the
-// source); the shell is stored as 24 "face quadrants" q = (principal axis p, sign of the principal
-// offset, signs of the two transverse offsets), each a square (r+1) x (r+1) patch of the plane
-// |d_p| = r indexed by the transverse distances (a, b).  A cell of plane r depends only on the
-// four cells (a-1|a, b-1|b) of plane r-1 of the same quadrant (column_density.f90:108-171).
+// source); the shell is stored as 6 faces (principal axis p, sign of the principal offset) of 4
+// quadrants (signs of the two transverse offsets), each a square (r+1) x (r+1) patch of the plane
+// |d_p| = r indexed by the transverse distances (a, b); the four quadrant values of (a,b) are
+// contiguous.  A cell of plane r depends only on the four cells (a-1|a, b-1|b) of plane r-1 of the
+// same quadrant (column_density.f90:108-171).
 struct RtParams {
   int n[3];                 // mesh
   int lim[3][2];            // [axis][0: negative side L, 1: positive side R], evolve_source.F90:100-102
   int subboxsize;
-  int plane_stride;         // S = max(lim)+1: global scratch holds 24*S*S doubles per plane buffer
+  int plane_stride;         // S = max(lim)+1: a global plane buffer holds 6 faces of raytrace_face_doubles(S)
   int smem_plane_doubles;   // capacity of one shared-memory plane buffer (single-CTA kernel)
   int smem_plane_doubles_cl;  // same for a CTA of the cluster kernel
   const double* tau_cell;   // sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens per cell
@@ -41,7 +42,7 @@ struct RtParams {
   const int* nseg_cl;
   int nwork;
   unsigned int* ticket;     // dynamic work counter (plays do_grid_master, master_slave.F90:124-231)
-  double* scratch;          // per-CTA global plane storage: [grid][2][24][S][S]
+  double* scratch;          // per-work-group global plane storage: [grid][2][6 faces][face_doubles]
   int* nbox_out;            // per source (global index)
   double* loss_out;         // per source
   double* coldens_dbg;      // optional full coldensh_out grid (debug/parity), or nullptr
@@ -76,6 +77,11 @@ void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, s
                     double eps, cudaStream_t stream);
 void launch_pair_table(const double* tab, double2* out, cudaStream_t stream);
 size_t raytrace_scratch_doubles_per_cta(int plane_stride);
+// doubles of one face (4 quadrants of S x S cells) of a global plane buffer, with slack for the reads of
+// zero-weight neighbours just outside the plane
+__host__ __device__ inline size_t raytrace_face_doubles(int plane_stride) {
+  return (size_t)4 * plane_stride * plane_stride + (size_t)8 * plane_stride + 32;
+}
 
 // ---- per-cell chemistry + fused statistics ------------------------------------------------------
 constexpr int kNumStat = 8;

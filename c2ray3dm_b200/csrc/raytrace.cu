@@ -9,27 +9,36 @@
 // guarantees the four upstream neighbours of a cell are finished first.  Those neighbours are
 // always one step closer to the source along every axis, and the ones that are not in the previous
 // Chebyshev shell carry an interpolation weight of exactly 0, so shell r depends on
-// shell r-1 only.  A shell further splits into 24 independent "face quadrants": principal axis p
-// (the dominant |offset|, which selects the cinterp branch), the sign of the principal offset and
-// the signs of the two transverse offsets.  In quadrant-local coordinates (a,b) = transverse
-// distances, the cell (a,b) of plane r reads (a-1|a, b-1|b) of plane r-1 of the SAME quadrant.
-// Cells shared between quadrants (on-axis a==0 / b==0, cube edges a==r / b==r) are computed by
-// every quadrant that needs them as an upstream value (the three cinterp branches agree on ties),
-// but only the quadrant the reference's branch order selects "owns" the cell: it alone adds the
-// rate into phih_grid and counts the boundary loss.
+// shell r-1 only.  A shell is the surface of a cube: 6 faces (principal axis p = the dominant
+// |offset|, which selects the cinterp branch, and the sign of the principal offset), each split into
+// 4 quadrants by the signs of the two transverse offsets.  In quadrant-local coordinates (a,b) =
+// transverse distances, the cell (a,b) of plane r reads (a-1|a, b-1|b) of plane r-1 of the SAME
+// quadrant.  Cells shared between quadrants (on-axis a==0 / b==0, cube edges a==r / b==r) are
+// computed by every quadrant that needs them as an upstream value (the three cinterp branches agree
+// on ties), but only the quadrant the reference's branch order selects "owns" the cell: it alone
+// adds the rate into phih_grid and counts the boundary loss.
 //
 // Mapping.  One work group per source, persistent work groups pulling sources from an atomic ticket
-// (the device-side do_grid_master, master_slave.F90:124-231).  A work group is one CTA of 256 threads
-// (three resident per SM) or, when there are too few long traces to fill the GPU that way, a
-// thread-block cluster of 8 CTAs, one per octant with its three face quadrants, whose boundary-loss
-// partial sums meet in rank 0's shared memory over DSMEM once per subbox pass.  Within a shell a
-// thread owns a column (quadrant q, transverse index a), or a b-segment of it, and walks b: the two
-// upstream values of its own column stay in registers from one b to the next, the two of column a-1
-// arrive by warp shuffle, so a cell costs one plane load, requested one row ahead together with the
-// grid value.  The planes of shell r-1 and r live in shared memory while they fit, afterwards in a
-// per-CTA global scratch.  The optical-depth table is staged in shared memory as (value, forward
-// difference) pairs.  Quadrants whose principal axis is x walk planes of constant x; they read and
-// accumulate into y-fastest twins of the grids so that their accesses are contiguous too.
+// (the device-side do_grid_master, master_slave.F90:124-231).  A work group is one CTA of 256
+// threads (two resident per SM) or, when there are too few long traces to fill the GPU that way, a
+// thread-block cluster of 6 CTAs, one per cube face, whose boundary-loss partial sums meet in rank
+// 0's shared memory over DSMEM once per subbox pass.  Within a shell a thread owns a column (face,
+// transverse index a), or a b-segment of it, and walks b, updating the FOUR quadrants of its face
+// together: the interpolation weights, the path length and the dilution volume depend only on
+// (r,a,b), so they are computed once per four cells, and the four dependency chains interleave in
+// the FP64 pipe.  The two upstream values of row b-1 stay in registers from one b to the next; row
+// b comes from the plane of shell r-1, which stores the four quadrant values of (a,b) contiguously
+// (32 bytes: two 128-bit loads fetch them).  The planes of shell r-1 and r live in shared memory
+// while they fit, afterwards in a per-CTA global scratch.  The optical-depth table is staged in
+// shared memory as (value, forward difference) pairs.  Faces whose principal axis is x walk planes
+// of constant x; they read and accumulate into y-fastest twins of the grids so that their accesses
+// are contiguous too.
+//
+// Upstream cells that do not exist in plane r-1 (a-1 < 0, b-1 < 0, a == r, b == r) are read as
+// whatever finite value the buffer holds: their bilinear weight is exactly 0 (the weights are built
+// so that a==r / b==r give exactly 1 and 0), so they do not contribute.  The plane buffers are
+// zero-filled once (shared memory at kernel start, the global scratch at allocation) and only ever
+// receive finite optical depths.
 //
 // Arithmetic.  The planes hold optical depths tau = sigma_HI * N_HI; the per-cell opacity
 // tau_cell = sigma_HI*dr(1)*max(1-max(xh_av,eps),eps)*ndens comes from a grid the per-cell kernel
@@ -51,12 +60,26 @@ namespace cg = cooperative_groups;
 namespace c2b {
 namespace {
 
-constexpr int kThreadsCta = 256;   // one CTA per source
-constexpr int kQuadrants = 24;
-#ifndef C2B_CTA_PER_SM
-#define C2B_CTA_PER_SM 3
-#endif
-constexpr int kCtaPerSm = C2B_CTA_PER_SM;   // resident CTAs per SM of the one-CTA-per-source kernel
+constexpr int kT = 256;            // threads per CTA
+constexpr int kFaces = 6;
+constexpr int kClusterSize = 6;    // the many-CTA work group: one CTA per face
+constexpr int kCtaPerSm = 2;
+constexpr int kPadFront = 8;       // doubles in front of every plane buffer (the a-1 read of column 0)
+
+// per-face constants of the current subbox pass, rebuilt in shared memory once per pass
+struct Face {
+  int srcP, srcA, srcB;       // 0-based source position along the principal / a / b axis
+  int nP, nA, nB;             // mesh extents along them
+  int sp;                     // sign of the principal offset
+  int p;                      // 0: z, 1: y, 2: x principal (the branch order of cinterp)
+  unsigned strP, strB;        // element strides of the principal and the b axis (the a axis is contiguous)
+  int limP;                   // extent of this pass's subbox along sp*P
+  int lrA, llA, lrB, llB;     // ... along +a, -a, +b, -b
+  int pad_;
+  double dP2, dA2, dB2;       // dr^2 per axis (dist2 of evolve_point.F90:170-174)
+  const double* tau;          // opacity grid (x-fastest, or the y-fastest twin for p == 2)
+  double* phih;               // rate grid, same layout
+};
 
 // max/min of two NON-NEGATIVE doubles through their bit patterns (integer order == numeric order there);
 // avoids the NaN-propagating DSETP.MAX/FSEL/LOP3 sequence fmax() and ?: compile to.
@@ -89,33 +112,43 @@ __device__ __forceinline__ double sel_max(double x, double y) {
   return r;
 }
 
+// constants of the table look-up kept in registers / uniform registers for the whole kernel
+struct LogC {
+  double c0, c1, c2, c3, c4, B;
+};
+
 // table coordinate odpos = 1 + (log10(max(1e-20,tau)) - minlogtau)/dlogtau of
 // set_tau_table_positions (radiation_photoionrates.F90:184-208), clamped to NumTau.
 // logtab[j] = {1/c_j, A + B*log2(c_j)}, c_j = 1 + (j+0.5)/128; coef = B/ln2 * {1,-1/2,1/3,-1/4,1/5}
-__device__ __forceinline__ double table_coord(double tau, const double2* __restrict__ logtab,
-                                              const RtParams& P) {
+__device__ __forceinline__ double table_coord(double tau, const double2* __restrict__ logtab, const LogC& L) {
   const double t = sel_max(tau, 1.0e-20);
   const int hi = __double2hiint(t);
   const int lo = __double2loint(t);
-  const int e = (hi >> 20) - 1023;
   const int j = (hi >> 13) & 127;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const double2 lt = logtab[j];
+  // (double)(exponent) without an integer->double conversion: 2^52 + (e + 2^31) as bits, minus 2^52 + 2^31
+  const double ed = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;
   const double rr = fma(m, lt.x, -1.0);
-  double q = fma(rr, P.logc[4], P.logc[3]);
-  q = fma(rr, q, P.logc[2]);
-  q = fma(rr, q, P.logc[1]);
-  q = fma(rr, q, P.logc[0]);
-  double od = fma(P.logB, (double)e, lt.y);
+  double q = fma(rr, L.c4, L.c3);
+  q = fma(rr, q, L.c2);
+  q = fma(rr, q, L.c1);
+  q = fma(rr, q, L.c0);
+  double od = fma(L.B, ed, lt.y);
   od = fma(rr, q, od);
   return pos_min(od, (double)kNumTau);  // od >= 0 because tau >= 1e-20
 }
 
-// read_table (radiation_photoionrates.F90:212-228) on the (value, forward difference) pairs
-__device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, double od) {
-  const int ipos = (int)od;
-  const double res = od - (double)ipos;
-  const double2 t = tab[ipos];
+// read_table (radiation_photoionrates.F90:212-228) on the (value, forward difference) pairs.
+// ipos = int(odpos), residual = odpos - ipos, by magic-number rounding of odpos-0.5 (no F2I/I2F);
+// at an exact integer odpos the pair (ipos-1, 1.0) may come out instead of (ipos, 0.0): same value.
+__device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, double od, int& ipos, double& res) {
+  const double sh = (od - 0.5) + 6755399441055744.0;
+  const int ip = __double2loint(sh);    // 0 <= od <= NumTau, so 0 <= ip <= NumTau
+  const double fl = sh - 6755399441055744.0;
+  ipos = ip;
+  res = od - fl;
+  const double2 t = tab[ip];
   return fma(t.y, res, t.x);
 }
 
@@ -123,33 +156,25 @@ __device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, do
 // Gamma_cell*vol_ph = F*(thick(tau_in)-thick(tau_out)), or F*dtau*thin(tau_in) below tau_photo_limit.
 __device__ __forceinline__ void photo_rates(double tau_in, double tau_out, double normflux,
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
-                                            const RtParams& P, double& phi_all, double& phi_out) {
-  const double od_in = table_coord(tau_in, s_logtab, P);
-  const double phi_in = normflux * lerp_pairs(s_thick, od_in);
+                                            const double* __restrict__ thin, double tau_photo_limit, const LogC& L,
+                                            double& phi_all, double& phi_out) {
+  const double od_in = table_coord(tau_in, s_logtab, L);
+  int ipos;
+  double res;
+  const double phi_in = normflux * lerp_pairs(s_thick, od_in, ipos, res);
   const double dtau = tau_out - tau_in;
-  if (fabs(dtau) > P.tau_photo_limit) {
-    const double od_out = table_coord(tau_out, s_logtab, P);
-    phi_out = normflux * lerp_pairs(s_thick, od_out);
+  if (fabs(dtau) > tau_photo_limit) {
+    const double od_out = table_coord(tau_out, s_logtab, L);
+    int ipos2;
+    double res2;
+    phi_out = normflux * lerp_pairs(s_thick, od_out, ipos2, res2);
     phi_all = phi_in - phi_out;
   } else {
-    const int ipos = (int)od_in;
-    const double res = od_in - (double)ipos;
-    const double lo = P.thin[ipos];
-    const double thin = lo + (P.thin[min(kNumTau, ipos + 1)] - lo) * res;
-    phi_all = normflux * dtau * thin;
+    const double lo = thin[ipos];
+    const double th = lo + (thin[min(kNumTau, ipos + 1)] - lo) * res;
+    phi_all = normflux * dtau * th;
     phi_out = phi_in - phi_all;
   }
-}
-
-// dist2 = xs*xs+ys*ys+zs*zs of evolve_point.F90:170-174 for the cell (principal offset r, transverse a, b).
-// Cubic cells (the reference's grids: dr(1)=dr(2)=dr(3)) need only dr^2 * (r^2+a^2+b^2) = dr^2 * q2; the general
-// form is evaluated on demand so that no per-axis factors stay live in the row loop.
-__device__ __forceinline__ double dist2_of(const RtParams& P, int p, int r, int a, double b2, double q2) {
-  if (P.cubic_cells) return P.dr2[0] * q2;
-  const double dP = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
-  const double dA = (p == 2) ? P.dr2[1] : P.dr2[0];
-  const double dB = (p == 0) ? P.dr2[1] : P.dr2[2];
-  return fma(dB, b2, fma(dP, (double)(r * r), dA * (double)(a * a)));
 }
 
 __device__ __forceinline__ int wrap(int x, int n) {
@@ -159,44 +184,248 @@ __device__ __forceinline__ int wrap(int x, int n) {
   return x;
 }
 
-// One CTA (kCluster == 1) or one cluster of 8 CTAs (kCluster == 8, one CTA per octant with its three
-// face quadrants) per source.
-// kLls: 0 = no LLS, 1 = homogeneous, 2 = LLS_grid, 3 = R_max barrier (LLS.F90:107-116); kDebug adds
-// the coldensh_out diagnostic store.
-// kGroups: the CTA's warps form kGroups independent groups, each owning kNq/kGroups quadrants and its own
-// named barrier, so a group waiting for its shell to complete does not idle the others.
-template <int kT, int kCluster, int kGroups, int kLls, bool kDebug>
-__global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm : 2) : 1) raytrace_kernel(RtParams P) {
-  constexpr int kNq = kQuadrants / kCluster;        // face quadrants handled by this CTA
-  constexpr int kNqg = kNq / kGroups;               // ... by one warp group
-  constexpr int kTg = kT / kGroups;                 // threads per group
-  static_assert(kNq % kGroups == 0 && kT % kGroups == 0 && kTg % 32 == 0, "bad group split");
+struct Quad {
+  double v[4];
+};
+__device__ __forceinline__ Quad load_quad(const double* p) {
+  const double2 lo = *reinterpret_cast<const double2*>(p);
+  const double2 hi = *reinterpret_cast<const double2*>(p + 2);
+  Quad q;
+  q.v[0] = lo.x; q.v[1] = lo.y; q.v[2] = hi.x; q.v[3] = hi.y;
+  return q;
+}
+__device__ __forceinline__ void store_quad(double* p, const Quad& q) {
+  *reinterpret_cast<double2*>(p) = make_double2(q.v[0], q.v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(q.v[2], q.v[3]);
+}
+
+// per-source values every thread of the work group holds
+struct SrcCtx {
+  double normflux;
+  int reach;      // subboxsize*nbox of this pass
+  int rsafe;      // shells r < rsafe are not clipped by the periodic half box on any side
+};
+
+// One shell of one source: the cells with Chebyshev distance r of the faces this CTA owns.
+// kGlobal: planes in the global scratch (else shared memory); kClip: the shell may touch the limits of
+// the subbox / half box; kR1: r == 1 (the sqrt(2)/sqrt(3) factors of column_density.f90:152-158).
+// kLls: 1 = homogeneous (tau_lls may be 0: no LLS), 2 = LLS_grid, 3 = R_max barrier (LLS.F90:107-116).
+template <int kNf, bool kGlobal, bool kClip, bool kR1, int kLls, bool kDebug>
+__device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, const Face* __restrict__ s_face,
+                                            const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
+                                            const LogC& L, int r, const double* __restrict__ prev,
+                                            double* __restrict__ cur, int nseg, double& loss) {
+  if (kGlobal) {
+    __builtin_assume(__isGlobal(prev));
+    __builtin_assume(__isGlobal(cur));
+  } else {
+    __builtin_assume(__isShared(prev));
+    __builtin_assume(__isShared(cur));
+  }
+  const int tid = threadIdx.x;
+  const int P1 = r + 1;
+  const int ncol = kNf * P1;
+  const int seglen = (P1 + nseg - 1) / nseg;
+  const int nitem = ncol * nseg;
+  const float inv_ncol = 1.0f / (float)ncol, inv_P1 = 1.0f / (float)P1;
+  const double rd = (double)r;
+  const double inv_r = fast_rcp(rd);
+  const double r2d = rd * rd;
+  const bool loss_shell = (r == S.reach);   // non-clipped shells: every cell of the shell is on the subbox boundary, or none
+  for (int it = tid; it < nitem; it += kT) {
+    // work item = (segment of b, face, column a), a fastest so that a warp spans adjacent columns
+    const int seg = (nseg == 1) ? 0 : (int)(((float)it + 0.5f) * inv_ncol);
+    const int c = it - seg * ncol;
+    const int fl = (kNf == 1) ? 0 : (int)(((float)c + 0.5f) * inv_P1);
+    const int a = c - fl * P1;
+    const Face& F = s_face[fl];
+    const int b0 = seg * seglen;
+    int bend = min(b0 + seglen - 1, r);
+    // ownership (see header): columns (a > 0 || sa > 0) && (p != 2 || a < r); bit j = quadrant (sa<0) | (sb<0)<<1
+    unsigned colmask = (a > 0) ? 0xFu : 0x5u;
+    if (F.p == 2 && a == r) colmask = 0u;
+    unsigned losscol = 0u;
+    if (kClip) {
+      if (r > F.limP) continue;                       // the face lies outside this pass's subbox
+      if (a > max(F.lrA, F.llA)) continue;
+      bend = min(bend, max(F.lrB, F.llB));
+      if (a > F.lrA) colmask &= ~0x5u;
+      if (a > F.llA) colmask &= ~0xAu;
+      // cells on the boundary of this pass's subbox (evolve_point.F90:290-295)
+      if (r == F.limP) losscol = 0xFu;
+      if (a == F.lrA) losscol |= 0x5u;
+      if (a == F.llA) losscol |= 0xAu;
+    }
+    if (!(S.normflux > 0.0)) colmask = 0u;            // a dark source is never traced (evolve_source.F90:119-131)
+    const int nrow = bend - b0 + 1;
+    if (nrow <= 0) continue;
+    const int own_hi = (F.p == 0) ? r : r - 1;        // b == r belongs to the z-principal face
+    // addresses: cell = posP*strP + posA + posB*strB
+    const unsigned rowP = (unsigned)wrap(F.srcP + F.sp * r, F.nP) * F.strP;
+    const unsigned baseAp = rowP + (unsigned)wrap(F.srcA + a, F.nA);
+    const unsigned baseAm = rowP + (unsigned)wrap(F.srcA - a, F.nA);
+    const int nB = F.nB;
+    const unsigned strB = F.strB;
+    int posBp = wrap(F.srcB + b0, nB), posBm = wrap(F.srcB - b0, nB);
+    const double* __restrict__ g_tau = F.tau;
+    double* __restrict__ g_phih = F.phih;
+    __builtin_assume(__isGlobal(g_tau));
+    __builtin_assume(__isGlobal(g_phih));
+    // column geometry shared by the four quadrants
+    const double ad = (double)a;
+    const double ua = (a == r) ? 1.0 : ad * inv_r;    // 1-dx of cinterp
+    const double va = 1.0 - ua;
+    const double a2d = ad * ad;
+    const double ca2 = r2d + a2d;
+    const double cA = fma(F.dP2, r2d, F.dA2 * a2d);
+    const double dB2 = F.dB2;
+    // planes: [face][b][a][quadrant]
+    const double* pp = prev + ((size_t)((fl * r + b0) * r + a) << 2);
+    double* pc = cur + ((size_t)((fl * P1 + b0) * P1 + a) << 2);
+    const int pstep = r << 2, cstep = P1 << 2;
+    Quad t1, t2;   // upstream values of row b-1: (a-1,b-1), (a,b-1)
+    if (b0 >= 1) {
+      t1 = load_quad(pp - pstep - 4);
+      t2 = load_quad(pp - pstep);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t1.v[j] = t2.v[j] = 0.0;
+    }
+    // software pipeline: the plane and grid values of the next row are requested one iteration ahead
+    Quad own_next = load_quad(pp);
+    unsigned offp = (unsigned)posBp * strB, offm = (unsigned)posBm * strB;
+    Quad tc_next;
+    tc_next.v[0] = g_tau[baseAp + offp];
+    tc_next.v[1] = g_tau[baseAm + offp];
+    tc_next.v[2] = g_tau[baseAp + offm];
+    tc_next.v[3] = g_tau[baseAm + offm];
+    double bd = (double)b0;
+    for (int k = 0; k < nrow; ++k) {
+      const int b = b0 + k;
+      const Quad t4 = own_next;               // (a, b)
+      const Quad t3 = load_quad(pp - 4);      // (a-1, b)
+      const Quad tc = tc_next;
+      const unsigned cellp = offp, cellm = offm;
+      // advance to row b+1 and request its inputs
+      pp += pstep;
+      posBp += 1;
+      offp += strB;
+      if (posBp == nB) { posBp = 0; offp = 0u; }
+      posBm -= 1;
+      offm -= strB;
+      if (posBm < 0) { posBm = nB - 1; offm = (unsigned)(nB - 1) * strB; }
+      if (k + 1 < nrow) {
+        own_next = load_quad(pp);
+        tc_next.v[0] = g_tau[baseAp + offp];
+        tc_next.v[1] = g_tau[baseAm + offp];
+        tc_next.v[2] = g_tau[baseAp + offm];
+        tc_next.v[3] = g_tau[baseAm + offm];
+      }
+      // ---- geometry of (r,a,b), common to the four quadrants --------------------------------------
+      const double ub = (b == r) ? 1.0 : bd * inv_r;  // 1-dy
+      const double vb = 1.0 - ub;
+      const double s1 = ua * ub, s2 = ub * va, s3 = ua * vb, s4 = va * vb;   // column_density.f90:137-149
+      const double b2 = bd * bd;
+      const double q2 = ca2 + b2;
+      const double rs = fast_rsqrt(q2);
+      const double pathc = q2 * rs * inv_r;                    // sqrt(1+(a^2+b^2)/r^2)
+      const double dist2 = fma(dB2, b2, cA);                   // evolve_point.F90:170-174
+      const double volk = P.fourpi_over_sigma * dist2 * pathc; // vol_ph*nHI = volk*tau_cell (:176-177)
+      bool stop_all = false;
+      if (kLls == 3) stop_all = dist2 > P.rmax_lls2;           // evolve_point.F90:186-196
+      double corr = 1.0;
+      if (kR1) corr = (a == 1 && b == 1) ? P.sqrt3 : ((a == 1 || b == 1) ? P.sqrt2 : 1.0);   // column_density.f90:152-158
+      unsigned rowmask = (b <= own_hi) ? ((b > 0) ? 0xFu : 0x3u) : 0u;
+      unsigned lossmask = losscol;
+      if (kClip) {
+        if (b > F.lrB) rowmask &= ~0x3u;
+        if (b > F.llB) rowmask &= ~0xCu;
+        if (b == F.lrB) lossmask |= 0x3u;
+        if (b == F.llB) lossmask |= 0xCu;
+      } else if (loss_shell) {
+        lossmask = 0xFu;
+      }
+      const unsigned ownmask = colmask & rowmask;
+      Quad out;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // cinterp, column_density.f90:108-171, with a common denominator; weightf = 1/max(0.6, tau), :276-293
+        const double m1 = sel_max(t1.v[j], 0.6), m2 = sel_max(t2.v[j], 0.6);
+        const double m3 = sel_max(t3.v[j], 0.6), m4 = sel_max(t4.v[j], 0.6);
+        const double p12 = m1 * m2, p34 = m3 * m4;
+        const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
+        const double num = fma(t1.v[j], e1, fma(t2.v[j], e2, fma(t3.v[j], e3, t4.v[j] * e4)));
+        const double den = (e1 + e2) + (e3 + e4);
+        double tau_in = num * fast_rcp(den);
+        if (kR1) tau_in *= corr;
+        const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
+        unsigned xcell = cell;   // x-fastest index of the cell, only for the grids that have no y-fastest twin
+        if ((kDebug || kLls == 2) && F.p == 2) {
+          const unsigned n1 = (unsigned)P.n[1], n2 = (unsigned)P.n[2];
+          const unsigned yy = cell % n1, xz = cell / n1;     // (x*n2 + z)*n1 + y
+          xcell = (xz % n2) * ((unsigned)P.n[0] * n1) + yy * (unsigned)P.n[0] + xz / n2;
+        }
+        if (kLls == 2) tau_in = fma((double)P.lls_grid[xcell] * P.sigma_HI, pathc, tau_in);
+        else if (kLls == 1) tau_in = fma(P.tau_lls, pathc, tau_in);
+        const double tau_cell = tc.v[j];
+        const double tau_out = fma(tau_cell, pathc, tau_in);       // evolve_point.F90:247-248
+        out.v[j] = tau_out;
+        if ((ownmask >> j) & 1u) {
+          if (kDebug) P.coldens_dbg[xcell] = tau_out * P.inv_sigma;
+          if (!(tau_in > P.tau_stop) && !stop_all) {                // :201
+            double phi_all, phi_out;
+            photo_rates(tau_in, tau_out, S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
+            // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI)
+            const double inv_vol = fast_rcp(volk * tau_cell);
+            const double photo_cell = phi_all * inv_vol;            // :262
+            if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);   // :283-284
+            // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
+            if ((lossmask >> j) & 1u) loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
+          }
+        }
+      }
+      store_quad(pc, out);
+      pc += cstep;
+      t1 = t3;
+      t2 = t4;
+      bd += 1.0;
+    }
+  }
+}
+
+// One CTA (kCluster == 1, all six faces) or one cluster of 6 CTAs (one face each) per source.
+template <int kCluster, int kLls, bool kDebug>
+__global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
+  constexpr int kNf = kFaces / kCluster;            // faces handled by this CTA
   extern __shared__ double2 smem2[];
   double2* s_thick = smem2;                         // kTableLen pairs
   double2* s_logtab = smem2 + kTableLen;            // 128 pairs
   double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128);
+  __shared__ Face s_face[kNf];
   __shared__ double s_red[kT / 32];
-  __shared__ double s_slot[2][8];                   // per-octant boundary loss, alternating by pass (rank 0's copy is used)
+  __shared__ double s_slot[2][8];                   // per-face boundary loss, alternating by pass (rank 0's copy is used)
   __shared__ int s_work;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int grp = tid / kTg;
-  const int gtid = tid - grp * kTg;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = (kCluster > 1) ? cluster.block_rank() : 0u;
-  const unsigned cid = (kCluster > 1) ? (blockIdx.x / kCluster) : blockIdx.x;   // work-group index
-  (void)cid;
+  const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;   // one shared plane buffer
   for (int i = tid; i < kTableLen; i += kT) s_thick[i] = P.thick2[i];
   for (int i = tid; i < 128; i += kT) s_logtab[i] = P.logtab[i];
-  // per group: two shared plane buffers of `cap` doubles and two global ones of kNqg*S*S
-  const int cap = (((kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl) / kGroups) & ~1;
-  double* s_planes_g = s_planes + (size_t)grp * 2 * cap;
-  const size_t gplane = (size_t)kNqg * P.plane_stride * P.plane_stride;
-  double* gbuf0 = P.scratch + ((size_t)blockIdx.x * kGroups + grp) * 2 * gplane;
-  double* gbuf1 = gbuf0 + gplane;
-  const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
-  const unsigned st1 = (unsigned)n0, st2 = (unsigned)n0 * (unsigned)n1;   // x-fastest strides of y and z
+  for (int i = tid; i < 2 * (cap + kPadFront); i += kT) s_planes[i] = 0.0;
+  double* sbuf0 = s_planes + kPadFront;
+  double* sbuf1 = sbuf0 + cap + kPadFront;
+  // global plane buffers: a slot of 2*6*Gf doubles per work group, Gf = one face
+  const size_t Gf = raytrace_face_doubles(P.plane_stride);
+  double* gbuf0;
+  if (kCluster == 1) gbuf0 = P.scratch + (size_t)blockIdx.x * 2 * kFaces * Gf + kPadFront;
+  else gbuf0 = P.scratch + ((size_t)(blockIdx.x / kCluster) * 2 * kFaces + 2 * crank) * Gf + kPadFront;
+  double* gbuf1 = gbuf0 + kNf * Gf;
+  LogC L;
+  L.c0 = P.logc[0]; L.c1 = P.logc[1]; L.c2 = P.logc[2]; L.c3 = P.logc[3]; L.c4 = P.logc[4]; L.B = P.logB;
+  SrcCtx S;
+  S.rsafe = min(min(min(P.lim[0][0], P.lim[0][1]), min(P.lim[1][0], P.lim[1][1])), min(P.lim[2][0], P.lim[2][1]));
   int pass_parity = 0;
 
   for (;;) {
@@ -214,219 +443,100 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
     if (w >= P.nwork) break;
     const int ns = P.work[w];  // 0-based source index
     const int src0 = P.srcpos[3 * ns] - 1, src1 = P.srcpos[3 * ns + 1] - 1, src2 = P.srcpos[3 * ns + 2] - 1;
-    const double normflux = P.normflux[ns];
-    const double total_source_flux = normflux * P.S_star;  // evolve_source.F90:119
+    S.normflux = P.normflux[ns];
+    const double total_source_flux = S.normflux * P.S_star;  // evolve_source.F90:119
 
     int nbox = 0;
     double photon_loss_src = total_source_flux;  // :121
     int lr0 = 0, lr1 = 0, lr2 = 0, ll0 = 0, ll1 = 0, ll2 = 0;  // last_r-src, src-last_l per axis
     int r_done = -1;
     // do while (evolve_source.F90:128-131); every thread of the work group evaluates it on identical values
-    while (photon_loss_src > P.loss_fraction * total_source_flux && lr2 < P.lim[2][1] &&
-           ll2 < P.lim[2][0]) {
+    while (photon_loss_src > P.loss_fraction * total_source_flux && lr2 < P.lim[2][1] && ll2 < P.lim[2][0]) {
       nbox += 1;
       const int reach = P.subboxsize * nbox;  // :135-136
+      S.reach = reach;
       lr0 = min(reach, P.lim[0][1]); ll0 = min(reach, P.lim[0][0]);
       lr1 = min(reach, P.lim[1][1]); ll1 = min(reach, P.lim[1][0]);
       lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
       const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
+      if (tid < kNf) {
+        // face f: p = f mod 3 (0: z, 1: y, 2: x principal), positive side first.
+        // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z) on the y-fastest twins (index (x*n2+z)*n1+y)
+        const int f = (int)crank * kNf + tid;
+        const int p = (f >= 3) ? f - 3 : f, sp = (f >= 3) ? -1 : 1;
+        const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
+        Face F;
+        F.p = p; F.sp = sp; F.pad_ = 0;
+        F.srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
+        F.srcA = (p == 2) ? src1 : src0;
+        F.srcB = (p == 0) ? src1 : src2;
+        F.nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
+        F.nA = (p == 2) ? n1 : n0;
+        F.nB = (p == 0) ? n1 : n2;
+        F.strP = (p == 0) ? (unsigned)n0 * (unsigned)n1 : (p == 1 ? (unsigned)n0 : (unsigned)n1 * (unsigned)n2);
+        F.strB = (p == 0) ? (unsigned)n0 : (p == 1 ? (unsigned)n0 * (unsigned)n1 : (unsigned)n1);
+        const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
+        F.limP = (sp > 0) ? lrP : llP;
+        F.lrA = (p == 2) ? lr1 : lr0; F.llA = (p == 2) ? ll1 : ll0;
+        F.lrB = (p == 0) ? lr1 : lr2; F.llB = (p == 0) ? ll1 : ll2;
+        F.dP2 = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
+        F.dA2 = (p == 2) ? P.dr2[1] : P.dr2[0];
+        F.dB2 = (p == 0) ? P.dr2[1] : P.dr2[2];
+        F.tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
+        F.phih = (p == 2) ? P.phih_t : P.phih;
+        s_face[tid] = F;
+      }
       double loss = 0.0;
       if (r_done < 0) {
         // shell 0 = the source cell (evolve_point.F90:151-160): coldensh_in=0, path=dr/2, vol_ph=cell volume.
-        // Every quadrant of the group stores it as its plane 0; the (+,+,+) z quadrant owns it.
-        if (gtid < kNqg) {
-          const int qc = grp * kNqg + gtid;
-          const int oct = (int)crank * (8 / kCluster) + qc / 3;
-          const unsigned cell = (unsigned)src2 * st2 + (unsigned)src1 * st1 + (unsigned)src0;
+        // Every quadrant stores it as its plane 0; the first thread of the +z face owns it.
+        if (tid < 4 * kNf) {
+          const unsigned cell = ((unsigned)src2 * (unsigned)P.n[1] + (unsigned)src1) * (unsigned)P.n[0] + (unsigned)src0;
           const double tau_cell = P.tau_cell[cell];
           const double tau_out = 0.5 * tau_cell;
-          s_planes_g[gtid] = tau_out;   // plane 0 always fits in shared memory
-          if (oct == 0 && qc - (qc / 3) * 3 == 0) {
+          sbuf0[tid] = tau_out;   // plane 0 always fits in shared memory
+          if (crank == 0 && tid == 0) {
             if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
-            if (normflux > 0.0) {
+            if (S.normflux > 0.0) {
               double phi_all, phi_out;
-              photo_rates(0.0, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
+              photo_rates(0.0, tau_out, S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
               // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
               const double photo_cell = phi_all * fast_rcp(P.vol_cell * tau_cell * P.inv_sigma_dr0);
               if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);
             }
           }
         }
-        if (kGroups == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kTg) : "memory");
         r_done = 0;
       }
+      __syncthreads();   // s_face and plane 0 visible
       for (int r = r_done + 1; r <= rmax; ++r) {
         const int P1 = r + 1;
-        // plane buffers of shell r (cur) and r-1 (prev): shared while they fit, else global scratch
-        double* cur = (kNqg * P1 * P1 <= cap) ? (s_planes_g + (r & 1) * cap) : ((r & 1) ? gbuf1 : gbuf0);
-        const double* prev = (kNqg * r * r <= cap) ? (s_planes_g + ((r - 1) & 1) * cap)
-                                                   : (((r - 1) & 1) ? gbuf1 : gbuf0);
-        const double inv_r = 1.0 / (double)r;
-        // work items: (segment of b, quadrant, column a), a fastest so that a warp spans adjacent columns
-        const int ncol = kNqg * P1;
         const int nseg = (kCluster == 1) ? P.nseg_cta[r] : P.nseg_cl[r];   // host-tuned split of the columns along b
-        const int seglen = (P1 + nseg - 1) / nseg;
-        const int nitem = ncol * nseg;
-        for (int it0 = gtid - lane; it0 < nitem; it0 += kTg) {  // warp-uniform trip count
-          const int it = it0 + lane;
-          const int seg = it / ncol;
-          const int c = it - seg * ncol;
-          const int ql = c / P1;
-          const int a = c - ql * P1;
-          // quadrant: the CTA (cluster rank) owns 8/kCluster octants, an octant has one quadrant per
-          // principal axis p (0: z, 1: y, 2: x = branch order of cinterp); octant bit0/1/2 = sign of x/y/z
-          const int qc = grp * kNqg + ql;
-          const int oct = (int)crank * (8 / kCluster) + qc / 3;
-          const int p = qc - (qc / 3) * 3;
-          const int sx = (oct & 1) ? -1 : 1, sy = (oct & 2) ? -1 : 1, sz = (oct & 4) ? -1 : 1;
-          const int sp = (p == 0) ? sz : (p == 1 ? sy : sx);
-          const int sa = (p == 2) ? sy : sx;
-          const int sb = (p == 0) ? sy : sz;
-          // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z)
-          const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
-          const int lrA = (p == 2) ? lr1 : lr0, llA = (p == 2) ? ll1 : ll0;
-          const int lrB = (p == 0) ? lr1 : lr2, llB = (p == 0) ? ll1 : ll2;
-          const bool col_ok = (it < nitem) && r <= (sp > 0 ? lrP : llP) && a <= (sa > 0 ? lrA : llA);
-          const int bmax = col_ok ? min(r, sb > 0 ? lrB : llB) : -1;
-          const int b0 = seg * seglen;
-          const int b1 = min(b0 + seglen - 1, r);      // last b of this segment (loop runs seglen times for all)
-          const int nB = (p == 0) ? n1 : n2;
-          const int nA = (p == 2) ? n1 : n0;
-          const int nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
-          const int srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
-          const int srcA = (p == 2) ? src1 : src0;
-          const int srcB = (p == 0) ? src1 : src2;
-          // x-principal quadrants walk planes of constant x: they use the y-fastest twins of the grids
-          // (index (x*n2 + z)*n1 + y) so that a warp's lanes (consecutive a = y) stay contiguous in memory
-          const unsigned strP = (p == 0) ? st2 : (p == 1 ? st1 : (unsigned)n1 * (unsigned)n2);
-          const unsigned strA = 1u;
-          const unsigned strideB = (p == 0) ? st1 : (p == 1 ? st2 : (unsigned)n1);
-          const double* __restrict__ g_tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
-          double* __restrict__ g_phih = (p == 2) ? P.phih_t : P.phih;
-          const unsigned base = (unsigned)wrap(srcP + sp * r, nP) * strP + (unsigned)wrap(srcA + sa * a, nA) * strA;
-          int posB = srcB + sb * b0;
-          if (posB < 0) posB += nB;
-          else if (posB >= nB) posB -= nB;
-          // the walk along b crosses the periodic boundary at most once: after kwrap more steps
-          const int kwrap = (sb > 0) ? (nB - 1 - posB) : posB;
-          // column-level geometry
-          const double ua = (double)a * inv_r;   // 1-dx of cinterp (a==r gives 1 to an ulp; the cells it would exclude read as 0)
-          const double ca2 = (double)(r * r + a * a);
-          // ownership pieces that do not depend on b (see header comment)
-          const bool own_col = (a > 0 || sa > 0) && (p != 2 || a < r);
-          // owned rows of this column: b in [own_lo, own_hi] (b==0 belongs to the sb>0 quadrant; b==r belongs
-          // to the z-principal quadrant)
-          const int own_lo = own_col ? ((sb > 0) ? 0 : 1) : 0x7fffffff;
-          const int own_hi = (p == 0) ? r : r - 1;
-          const int loss_b = (sb > 0) ? lrB : llB;     // row on the subbox boundary (any row if the column is)
-          const bool loss_col = (sp > 0 ? r == lrP : r == llP) || (sa * a == lrA) || (sa * a == -llA);
-          const bool a_in = a <= r - 1;           // column a exists in plane r-1
-          const int blast = min(bmax, r - 1);     // last b with an upstream value in this column
-          const int nact = max(0, min(b1, bmax) - b0 + 1);   // cells of this segment that exist
-          const int nup = max(0, min(b1, blast) - b0 + 1);   // ... that have an upstream cell (a|a-1, b)
-          const double* pown = prev + ql * r * r + b0 * r + a;   // plane r-1 patch (stride r), row b0
-          double* pout = cur + ql * P1 * P1 + b0 * P1 + a;       // plane r patch (stride r+1)
-          // carried upstream values of row b0-1
-          double c_own_bm1 = 0.0, c_left_bm1 = 0.0;
-          if (b0 >= 1 && b0 - 1 <= blast) {
-            if (a_in) c_own_bm1 = pown[-r];
-            if (a >= 1) c_left_bm1 = pown[-r - 1];
+        // a plane of side s fits a shared buffer together with the slack the zero-weight reads may touch
+        const bool cur_sm = 4 * kNf * P1 * P1 + 4 * P1 + 8 <= cap;
+        bool prev_sm = 4 * kNf * r * r + 4 * r + 8 <= cap;
+        if (cur_sm) {
+          double* cur = (r & 1) ? sbuf1 : sbuf0;
+          const double* prev = (r & 1) ? sbuf0 : sbuf1;
+          if (r == 1) trace_shell<kNf, false, false, true, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
+          else if (r < S.rsafe) trace_shell<kNf, false, false, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
+          else trace_shell<kNf, false, true, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
+        } else {
+          double* cur = (r & 1) ? gbuf1 : gbuf0;
+          double* gprev = (r & 1) ? gbuf0 : gbuf1;
+          if (prev_sm) {
+            // first shell that does not fit: move plane r-1 to the global scratch
+            const double* sprev = (r & 1) ? sbuf0 : sbuf1;
+            const int nmove = 4 * kNf * r * r;
+            for (int i = tid; i < nmove; i += kT) gprev[i] = sprev[i];
+            __syncthreads();
+            prev_sm = false;
           }
-          // software pipeline: the plane and grid values of the next cell are requested one iteration ahead
-          unsigned cell_next = base + (unsigned)posB * strideB;
-          double tau_cell_next = 0.0, c_own_next = 0.0, c_lane0_next = 0.0;
-          if (nact > 0) tau_cell_next = g_tau[cell_next];
-          if (a_in && nup > 0) c_own_next = pown[0];
-          if (lane == 0 && a >= 1 && nup > 0) c_lane0_next = pown[-1];
-          double bd = (double)b0;
-          const int dcell = sb * (int)strideB;
-          const int dcell_wrap = dcell - sb * (int)strideB * nB;   // step that crosses the boundary
-          for (int k = 0; k < seglen; ++k) {
-            const int b = b0 + k;
-            const bool active = k < nact;
-            // upstream optical depths (cells outside plane r-1 have weight 0; read as 0)
-            const double c_own = c_own_next;
-            double c_left = __shfl_up_sync(0xffffffffu, c_own, 1);
-            if (lane == 0) c_left = c_lane0_next;
-            if (a == 0) c_left = 0.0;
-            const double t1 = c_left_bm1, t2 = c_own_bm1, t3 = c_left, t4 = c_own;
-            c_left_bm1 = c_left;
-            c_own_bm1 = c_own;
-            const unsigned cell = cell_next;
-            const double tau_cell = tau_cell_next;
-            // advance to row b+1 and request its inputs
-            pown += r;
-            cell_next = (unsigned)((int)cell + ((k == kwrap) ? dcell_wrap : dcell));
-            c_own_next = 0.0;
-            if (k + 1 < nact) tau_cell_next = g_tau[cell_next];
-            if (k + 1 < nup) {
-              if (a_in) c_own_next = pown[0];
-              if (lane == 0 && a >= 1) c_lane0_next = pown[-1];
-            } else {
-              c_lane0_next = 0.0;
-            }
-            if (active) {
-              bool stop = false;
-              // x-fastest index of the cell, only for the grids that have no y-fastest twin
-              unsigned xcell = 0;
-              if ((kDebug || kLls == 2) && p == 2) {
-                const unsigned t = cell;                    // (x*n2 + z)*n1 + y
-                const unsigned yy = t % (unsigned)n1, xz = t / (unsigned)n1;
-                xcell = (xz % (unsigned)n2) * st2 + yy * st1 + xz / (unsigned)n2;
-              }
-              // cinterp, column_density.f90:108-171, with a common denominator
-              const double ub = bd * inv_r;  // 1-dy
-              const double va = 1.0 - ua, vb = 1.0 - ub;
-              const double s1 = ua * ub, s2 = ub * va, s3 = ua * vb, s4 = va * vb;
-              // weightf = 1/max(0.6, tau), column_density.f90:276-293
-              const double m1 = sel_max(t1, 0.6), m2 = sel_max(t2, 0.6);
-              const double m3 = sel_max(t3, 0.6), m4 = sel_max(t4, 0.6);
-              const double p12 = m1 * m2, p34 = m3 * m4;
-              const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
-              const double num = fma(t1, e1, fma(t2, e2, fma(t3, e3, t4 * e4)));
-              const double den = (e1 + e2) + (e3 + e4);
-              double tau_in = num * fast_rcp(den);
-              if (r == 1 && (a == 1 || b == 1)) tau_in *= (a == 1 && b == 1) ? P.sqrt3 : P.sqrt2;  // :152-158
-              const double b2 = bd * bd;
-              const double q2 = ca2 + b2;
-              const double rs = fast_rsqrt(q2);
-              const double pathc = q2 * rs * inv_r;                        // sqrt(1+(a^2+b^2)/r^2)
-              if (kLls == 3) {  // evolve_point.F90:186-196
-                if (dist2_of(P, p, r, a, b2, q2) > P.rmax_lls2) stop = true;
-              } else if (kLls == 2) {
-                tau_in = fma((double)P.lls_grid[(p == 2) ? xcell : cell] * P.sigma_HI, pathc, tau_in);
-              } else if (kLls == 1) {
-                tau_in = fma(P.tau_lls, pathc, tau_in);
-              }
-              if (tau_in > P.tau_stop) stop = true;                          // :201
-              const double tau_out = fma(tau_cell, pathc, tau_in);         // :247-248
-              *pout = tau_out;
-              const bool owner = (b >= own_lo) && (b <= own_hi);
-              if (owner) {
-                if (kDebug) P.coldens_dbg[(p == 2) ? xcell : cell] = tau_out * P.inv_sigma;
-                if (!stop && normflux > 0.0) {
-                  double phi_all, phi_out;
-                  photo_rates(tau_in, tau_out, normflux, s_thick, s_logtab, P, phi_all, phi_out);
-                  // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI) = phi_all/volfac
-                  const double dist2 = dist2_of(P, p, r, a, b2, q2);
-                  const double volfac = P.fourpi_over_sigma * dist2 * pathc * tau_cell;
-                  const double inv_vol = fast_rcp(volfac);
-                  const double photo_cell = phi_all * inv_vol;             // evolve_point.F90:262
-                  if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);  // :283-284
-                  // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
-                  if (loss_col || b == loss_b)
-                    loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
-                }
-              }
-            }
-            pout += P1;
-            bd += 1.0;
-          }
+          if (r == 1) trace_shell<kNf, true, false, true, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
+          else if (r < S.rsafe) trace_shell<kNf, true, false, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
+          else trace_shell<kNf, true, true, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
         }
-        // plane r complete before plane r+1 reads it (quadrants never cross groups)
-        if (kGroups == 1) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kTg) : "memory");
+        __syncthreads();   // plane r complete before plane r+1 reads it (quadrants never cross CTAs)
       }
       r_done = rmax;
       // photon_loss_src = sum over the work group (plays photon_loss_src_thread, evolve_source.F90:183-186)
@@ -447,10 +557,11 @@ __global__ void __launch_bounds__(kT, (kT <= 256) ? ((kCluster == 1) ? kCtaPerSm
         cluster.sync();
         const double* slots = cluster.map_shared_rank(&s_slot[pass_parity][0], 0);
         double t = 0.0;
-        for (int i = 0; i < kCluster; ++i) t += slots[i];   // fixed order: identical in all 8 CTAs
+        for (int i = 0; i < kCluster; ++i) t += slots[i];   // fixed order: identical in all CTAs
         photon_loss_src = t;
         pass_parity ^= 1;
       }
+      __syncthreads();   // s_red / s_face are rewritten by the next pass
     }
     if (crank == 0 && tid == 0) {
       P.nbox_out[ns] = nbox;              // sum_nbox=sum_nbox+nbox, :219
@@ -482,57 +593,41 @@ __global__ void pair_table_kernel(const double* __restrict__ tab, double2* __res
 }  // namespace
 
 size_t raytrace_scratch_doubles_per_cta(int plane_stride) {
-  // sized for the single-CTA kernel (24 quadrants); a cluster CTA uses 3 of them
-  return (size_t)2 * kQuadrants * plane_stride * plane_stride;
+  // one work-group slot: two plane buffers of six faces
+  return (size_t)2 * kFaces * raytrace_face_doubles(plane_stride);
 }
 
 static size_t rt_smem_bytes(int plane_doubles) {
-  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * plane_doubles * sizeof(double);
+  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * (plane_doubles + kPadFront) * sizeof(double);
 }
 
 typedef void (*RtKernel)(RtParams);
 
-template <int kT, int kCluster, int kGroups>
+template <int kCluster>
 static RtKernel pick_kernel(int lls, bool debug) {
   if (debug) {
     switch (lls) {
-      case 0: return raytrace_kernel<kT, kCluster, kGroups, 0, true>;
-      case 1: return raytrace_kernel<kT, kCluster, kGroups, 1, true>;
-      case 2: return raytrace_kernel<kT, kCluster, kGroups, 2, true>;
-      default: return raytrace_kernel<kT, kCluster, kGroups, 3, true>;
+      case 2: return raytrace_kernel<kCluster, 2, true>;
+      case 3: return raytrace_kernel<kCluster, 3, true>;
+      default: return raytrace_kernel<kCluster, 1, true>;
     }
   }
   switch (lls) {
-    case 0: return raytrace_kernel<kT, kCluster, kGroups, 0, false>;
-    case 1: return raytrace_kernel<kT, kCluster, kGroups, 1, false>;
-    case 2: return raytrace_kernel<kT, kCluster, kGroups, 2, false>;
-    default: return raytrace_kernel<kT, kCluster, kGroups, 3, false>;
+    case 2: return raytrace_kernel<kCluster, 2, false>;
+    case 3: return raytrace_kernel<kCluster, 3, false>;
+    default: return raytrace_kernel<kCluster, 1, false>;
   }
 }
 
-// work-group shapes of the many-CTA kernel (C2B_CLUSTER_VARIANT selects one)
-struct ClusterVariant {
-  int threads, cluster, groups;
-  RtKernel (*pick)(int, bool);
-  int ctas_per_sm() const { return threads <= 256 ? 2 : 1; }
-};
-static const ClusterVariant kVariants[] = {
-    {512, 8, 1, pick_kernel<512, 8, 1>},  // 0: one octant per CTA, one CTA per SM (planes in shared memory up to r = 63)
-    {480, 8, 3, pick_kernel<480, 8, 3>},  // 1: as 0 with one warp group (own named barrier) per face quadrant
-    {256, 8, 1, pick_kernel<256, 8, 1>},  // 2: one octant per CTA, two CTAs (two sources) per SM  [default]
-    {256, 2, 1, pick_kernel<256, 2, 1>},  // 3: four octants per CTA, two CTAs per SM
-};
-static int g_variant = 2;
-
-static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, const ClusterVariant& v, int nclusters,
-                           size_t smem, cudaStream_t stream) {
+static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int nclusters, size_t smem,
+                           cudaStream_t stream) {
   *cfg = cudaLaunchConfig_t{};
-  cfg->gridDim = dim3(v.cluster * nclusters, 1, 1);
-  cfg->blockDim = dim3(v.threads, 1, 1);
+  cfg->gridDim = dim3(kClusterSize * nclusters, 1, 1);
+  cfg->blockDim = dim3(kT, 1, 1);
   cfg->dynamicSmemBytes = smem;
   cfg->stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = v.cluster;
+  attr[0].val.clusterDim.x = kClusterSize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg->attrs = attr;
@@ -545,60 +640,53 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (const char* env = getenv("C2B_CLUSTER_VARIANT")) {
-    const int v = atoi(env);
-    if (v >= 0 && v < (int)(sizeof(kVariants) / sizeof(kVariants[0]))) g_variant = v;
-  }
-  const ClusterVariant& V = kVariants[g_variant];
-  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
-  // ---- single-CTA kernel: two CTAs per SM share the opt-in shared memory ----------------------
-  const int per_cta = std::min(max_optin, sm_total / kCtaPerSm - 2048);
+  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2) + 2 * kPadFront * sizeof(double);
+  // kCtaPerSm CTAs per SM share the opt-in shared memory; what the tables leave goes to the two plane buffers
+  int per_cta = std::min(max_optin, sm_total / kCtaPerSm - 2048);
+  if (const char* env = getenv("C2B_RT_SMEM_KB")) per_cta = std::min(per_cta, atoi(env) * 1024);
   int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
-  cap = std::min(cap, kQuadrants * (max_radius + 1) * (max_radius + 1)) & ~1;
-  // ---- cluster kernel: one CTA per SM with all of the opt-in shared memory ----------------------
-  const int per_cta_cl = (V.ctas_per_sm() == 2) ? std::min(max_optin, sm_total / 2 - 2048) : max_optin;
-  int cap_cl = (int)(((size_t)per_cta_cl - fixed - 2048) / (2 * sizeof(double)));
-  cap_cl = std::min(cap_cl, (kQuadrants / V.cluster) * (max_radius + 1) * (max_radius + 1) + 2 * V.groups) & ~1;
+  const int full = 4 * kFaces * (max_radius + 1) * (max_radius + 1);
+  const int slack = 4 * (max_radius + 1) + 8;
+  const int cap_cta = std::max(128, std::min(cap, full + slack)) & ~3;
+  const int cap_cl = std::max(128, std::min(cap, full / kClusterSize + slack)) & ~3;
   for (int dbg = 0; dbg < 2; ++dbg)
-    for (int lls = 0; lls < 4; ++lls) {
-      cudaError_t e = cudaFuncSetAttribute(pick_kernel<kThreadsCta, 1, 1>(lls, dbg != 0),
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes(cap));
+    for (int lls = 1; lls < 4; ++lls) {
+      cudaError_t e = cudaFuncSetAttribute(pick_kernel<1>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)rt_smem_bytes(cap_cta));
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(V.pick(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(pick_kernel<kClusterSize>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)rt_smem_bytes(cap_cl));
       if (e != cudaSuccess) return (int)e;
     }
-  info->smem_plane_doubles = cap;
+  info->smem_plane_doubles = cap_cta;
   info->smem_plane_doubles_cl = cap_cl;
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<kThreadsCta, 1, 1>(1, false), kThreadsCta,
-                                                rt_smem_bytes(cap));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<1>(1, false), kT, rt_smem_bytes(cap_cta));
   info->grid_cta = sms * std::max(1, per_sm);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, V, sms, rt_smem_bytes(cap_cl), nullptr);
+  cluster_config(&cfg, attr, sms, rt_smem_bytes(cap_cl), nullptr);
   int nclusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, V.pick(1, false), &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, pick_kernel<kClusterSize>(1, false), &cfg);
   if (e != cudaSuccess) return (int)e;
   info->clusters = std::max(1, nclusters);
-  info->cluster_size = V.cluster;
-  // scratch slots of 2*24*S*S doubles: one per resident CTA of the single-CTA kernel plus one per resident
-  // cluster (its CTAs share a slot: 24/cluster quadrants each)
+  info->cluster_size = kClusterSize;
+  // scratch slots: one per resident CTA of the single-CTA kernel plus one per resident cluster
   info->grid_max = info->grid_cta + info->clusters;
   return 0;
 }
 
-// Number of b-segments per column for shell r: minimises rounds x (segment length + set-up) for a group
-// of `threads` threads that owns `nq` quadrants, i.e. nq*(r+1) columns.
-static void build_nseg_table(int max_radius, int nq, int threads, std::vector<int>& tab) {
+// Number of b-segments per column for shell r: minimises rounds x (segment length + set-up) for a CTA
+// that owns `nf` faces, i.e. nf*(r+1) columns of four cells per row.
+static void build_nseg_table(int max_radius, int nf, int threads, std::vector<int>& tab) {
   tab.assign((size_t)max_radius + 2, 1);
   for (int r = 1; r <= max_radius; ++r) {
-    const int P1 = r + 1, ncol = nq * P1;
+    const int P1 = r + 1, ncol = nf * P1;
     long best = -1;
     int best_n = 1;
-    for (int n = 1; n <= std::max(1, P1 / 2) && n <= 64; ++n) {
+    for (int n = 1; n <= P1 && n <= 64; ++n) {
       const long rounds = ((long)ncol * n + threads - 1) / threads;
-      const long cost = rounds * ((P1 + n - 1) / n + 2);
+      const long cost = rounds * (2 * ((P1 + n - 1) / n) + 3);   // a row costs ~2 set-ups' worth... set-up ~1.5 rows
       if (best < 0 || cost < best) { best = cost; best_n = n; }
     }
     tab[r] = best_n;
@@ -606,24 +694,21 @@ static void build_nseg_table(int max_radius, int nq, int threads, std::vector<in
 }
 
 void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl) {
-  const ClusterVariant& V = kVariants[g_variant];
-  build_nseg_table(max_radius, kQuadrants, kThreadsCta, cta);
-  build_nseg_table(max_radius, kQuadrants / V.cluster / V.groups, V.threads / V.groups, cl);
+  build_nseg_table(max_radius, kFaces, kT, cta);
+  build_nseg_table(max_radius, 1, kT, cl);
 }
 
 static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  pick_kernel<kThreadsCta, 1, 1>(lls_mode(p), p.coldens_dbg != nullptr)
-      <<<grid, kThreadsCta, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+  pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
 }
 
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {
-  const ClusterVariant& V = kVariants[g_variant];
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, V, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl), stream);
-  return (int)cudaLaunchKernelEx(&cfg, V.pick(lls_mode(p), p.coldens_dbg != nullptr), p);
+  cluster_config(&cfg, attr, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl), stream);
+  return (int)cudaLaunchKernelEx(&cfg, pick_kernel<kClusterSize>(lls_mode(p), p.coldens_dbg != nullptr), p);
 }
 
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
