@@ -158,23 +158,30 @@ __device__ __forceinline__ void photo_rates(double tau_in, double tau_out, doubl
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
                                             const double* __restrict__ thin, double tau_photo_limit, const LogC& L,
                                             double& phi_all, double& phi_out) {
+  // both table coordinates are formed together (two independent chains); the thin branch overrides
   const double od_in = table_coord(tau_in, s_logtab, L);
-  int ipos;
-  double res;
+  const double od_out = table_coord(tau_out, s_logtab, L);
+  int ipos, ipos2;
+  double res, res2;
   const double phi_in = normflux * lerp_pairs(s_thick, od_in, ipos, res);
+  phi_out = normflux * lerp_pairs(s_thick, od_out, ipos2, res2);
+  phi_all = phi_in - phi_out;
   const double dtau = tau_out - tau_in;
-  if (fabs(dtau) > tau_photo_limit) {
-    const double od_out = table_coord(tau_out, s_logtab, L);
-    int ipos2;
-    double res2;
-    phi_out = normflux * lerp_pairs(s_thick, od_out, ipos2, res2);
-    phi_all = phi_in - phi_out;
-  } else {
+  if (!(fabs(dtau) > tau_photo_limit)) {
     const double lo = thin[ipos];
     const double th = lo + (thin[min(kNumTau, ipos + 1)] - lo) * res;
     phi_all = normflux * dtau * th;
     phi_out = phi_in - phi_all;
   }
+}
+
+// x-fastest index of a cell addressed in the layout of face p (p == 2: the y-fastest twin, (x*n2 + z)*n1 + y);
+// only for the grids that have no y-fastest twin (LLS_grid, the coldensh_out diagnostic)
+__device__ __forceinline__ unsigned xfast_index(const RtParams& P, int p, unsigned cell) {
+  if (p != 2) return cell;
+  const unsigned n1 = (unsigned)P.n[1], n2 = (unsigned)P.n[2];
+  const unsigned yy = cell % n1, xz = cell / n1;
+  return (xz % n2) * ((unsigned)P.n[0] * n1) + yy * (unsigned)P.n[0] + xz / n2;
 }
 
 __device__ __forceinline__ int wrap(int x, int n) {
@@ -346,7 +353,8 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
         lossmask = 0xFu;
       }
       const unsigned ownmask = colmask & rowmask;
-      Quad out;
+      // ---- phase A: interpolation of the four quadrants, branch-free so that the four chains interleave ----
+      Quad tin, out;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         // cinterp, column_density.f90:108-171, with a common denominator; weightf = 1/max(0.6, tau), :276-293
@@ -358,23 +366,25 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
         const double den = (e1 + e2) + (e3 + e4);
         double tau_in = num * fast_rcp(den);
         if (kR1) tau_in *= corr;
-        const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
-        unsigned xcell = cell;   // x-fastest index of the cell, only for the grids that have no y-fastest twin
-        if ((kDebug || kLls == 2) && F.p == 2) {
-          const unsigned n1 = (unsigned)P.n[1], n2 = (unsigned)P.n[2];
-          const unsigned yy = cell % n1, xz = cell / n1;     // (x*n2 + z)*n1 + y
-          xcell = (xz % n2) * ((unsigned)P.n[0] * n1) + yy * (unsigned)P.n[0] + xz / n2;
+        if (kLls == 2) {
+          const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
+          tau_in = fma((double)P.lls_grid[xfast_index(P, F.p, cell)] * P.sigma_HI, pathc, tau_in);
+        } else if (kLls == 1) {
+          tau_in = fma(P.tau_lls, pathc, tau_in);
         }
-        if (kLls == 2) tau_in = fma((double)P.lls_grid[xcell] * P.sigma_HI, pathc, tau_in);
-        else if (kLls == 1) tau_in = fma(P.tau_lls, pathc, tau_in);
-        const double tau_cell = tc.v[j];
-        const double tau_out = fma(tau_cell, pathc, tau_in);       // evolve_point.F90:247-248
-        out.v[j] = tau_out;
+        tin.v[j] = tau_in;
+        out.v[j] = fma(tc.v[j], pathc, tau_in);       // evolve_point.F90:247-248
+      }
+      // ---- phase B: rates of the cells this face owns and that are not behind the 2e19 column (:201) ------
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         if ((ownmask >> j) & 1u) {
-          if (kDebug) P.coldens_dbg[xcell] = tau_out * P.inv_sigma;
-          if (!(tau_in > P.tau_stop) && !stop_all) {                // :201
+          const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
+          if (kDebug) P.coldens_dbg[xfast_index(P, F.p, cell)] = out.v[j] * P.inv_sigma;
+          if (!(tin.v[j] > P.tau_stop) && !stop_all) {
+            const double tau_cell = tc.v[j];
             double phi_all, phi_out;
-            photo_rates(tau_in, tau_out, S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
+            photo_rates(tin.v[j], out.v[j], S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
             // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI)
             const double inv_vol = fast_rcp(volk * tau_cell);
             const double photo_cell = phi_all * inv_vol;            // :262
