@@ -60,10 +60,29 @@ namespace cg = cooperative_groups;
 namespace c2b {
 namespace {
 
-constexpr int kT = 256;            // threads per CTA
+#ifndef C2B_RT_THREADS
+#define C2B_RT_THREADS 256
+#endif
+#ifndef C2B_CTA_PER_SM
+#define C2B_CTA_PER_SM 2
+#endif
+constexpr int kT = C2B_RT_THREADS; // threads per CTA
 constexpr int kFaces = 6;
 constexpr int kClusterSize = 6;    // the many-CTA work group: one CTA per face
-constexpr int kCtaPerSm = 2;
+constexpr int kCtaPerSm = C2B_CTA_PER_SM;
+constexpr int kWarps = kT / 32;
+#ifndef C2B_RT_ILP
+#define C2B_RT_ILP 4
+#endif
+constexpr int kIlp = C2B_RT_ILP;   // quadrants whose interpolation chains are interleaved (4, 2 or 1)
+// The six faces of a source never exchange data, so a CTA walks them in independent groups of kFpg faces, each
+// group with kT/(6/kFpg) threads and its own barrier (a warp barrier when the group is one warp).
+#ifndef C2B_RT_FPG
+#define C2B_RT_FPG 6
+#endif
+constexpr int kFpgCta = C2B_RT_FPG;                      // faces per group, single-CTA kernel
+constexpr int kTgCta = kT / (kFaces / kFpgCta);          // threads per group
+static_assert(kFaces % kFpgCta == 0 && kT % (kFaces / kFpgCta) == 0 && kTgCta % 32 == 0, "bad face grouping");
 constexpr int kPadFront = 8;       // doubles in front of every plane buffer (the a-1 read of column 0)
 
 // per-face constants of the current subbox pass, rebuilt in shared memory once per pass
@@ -191,6 +210,14 @@ __device__ __forceinline__ int wrap(int x, int n) {
   return x;
 }
 
+// synchronises the kTg threads of face group g
+template <int kTg>
+__device__ __forceinline__ void group_sync(int g) {
+  if (kTg == 32) __syncwarp();
+  else if (kTg == kT) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kTg) : "memory");
+}
+
 struct Quad {
   double v[4];
 };
@@ -217,11 +244,14 @@ struct SrcCtx {
 // kGlobal: planes in the global scratch (else shared memory); kClip: the shell may touch the limits of
 // the subbox / half box; kR1: r == 1 (the sqrt(2)/sqrt(3) factors of column_density.f90:152-158).
 // kLls: 1 = homogeneous (tau_lls may be 0: no LLS), 2 = LLS_grid, 3 = R_max barrier (LLS.F90:107-116).
-template <int kNf, bool kGlobal, bool kClip, bool kR1, int kLls, bool kDebug>
-__device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, const Face* __restrict__ s_face,
+// The kFpg faces `faces[0..kFpg)` are walked by kTg threads (this thread is number `gtid`); prev/cur are the plane
+// buffers of the first face, those of the next faces follow at `fstride` doubles.  min_hi returns the high word of
+// the smallest optical depth written (the dead-face rule in the kernel).
+template <int kFpg, int kTg, bool kGlobal, bool kClip, bool kR1, int kLls, bool kDebug>
+__device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, const Face* __restrict__ faces, int gtid,
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
                                             const LogC& L, int r, const double* __restrict__ prev,
-                                            double* __restrict__ cur, int nseg, double& loss) {
+                                            double* __restrict__ cur, int fstride, int nseg, double& loss, int& min_hi) {
   if (kGlobal) {
     __builtin_assume(__isGlobal(prev));
     __builtin_assume(__isGlobal(cur));
@@ -229,23 +259,22 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
     __builtin_assume(__isShared(prev));
     __builtin_assume(__isShared(cur));
   }
-  const int tid = threadIdx.x;
   const int P1 = r + 1;
-  const int ncol = kNf * P1;
   const int seglen = (P1 + nseg - 1) / nseg;
+  const int ncol = kFpg * P1;
   const int nitem = ncol * nseg;
   const float inv_ncol = 1.0f / (float)ncol, inv_P1 = 1.0f / (float)P1;
   const double rd = (double)r;
   const double inv_r = fast_rcp(rd);
   const double r2d = rd * rd;
   const bool loss_shell = (r == S.reach);   // non-clipped shells: every cell of the shell is on the subbox boundary, or none
-  for (int it = tid; it < nitem; it += kT) {
+  for (int it = gtid; it < nitem; it += kTg) {
     // work item = (segment of b, face, column a), a fastest so that a warp spans adjacent columns
     const int seg = (nseg == 1) ? 0 : (int)(((float)it + 0.5f) * inv_ncol);
     const int c = it - seg * ncol;
-    const int fl = (kNf == 1) ? 0 : (int)(((float)c + 0.5f) * inv_P1);
-    const int a = c - fl * P1;
-    const Face& F = s_face[fl];
+    const int flg = (kFpg == 1) ? 0 : (int)(((float)c + 0.5f) * inv_P1);
+    const int a = c - flg * P1;
+    const Face& F = faces[flg];
     const int b0 = seg * seglen;
     int bend = min(b0 + seglen - 1, r);
     // ownership (see header): columns (a > 0 || sa > 0) && (p != 2 || a < r); bit j = quadrant (sa<0) | (sb<0)<<1
@@ -286,9 +315,9 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
     const double ca2 = r2d + a2d;
     const double cA = fma(F.dP2, r2d, F.dA2 * a2d);
     const double dB2 = F.dB2;
-    // planes: [face][b][a][quadrant]
-    const double* pp = prev + ((size_t)((fl * r + b0) * r + a) << 2);
-    double* pc = cur + ((size_t)((fl * P1 + b0) * P1 + a) << 2);
+    // planes of this face: [b][a][quadrant]
+    const double* pp = prev + flg * fstride + ((b0 * r + a) << 2);
+    double* pc = cur + flg * fstride + ((b0 * P1 + a) << 2);
     const int pstep = r << 2, cstep = P1 << 2;
     Quad t1, t2;   // upstream values of row b-1: (a-1,b-1), (a,b-1)
     if (b0 >= 1) {
@@ -353,44 +382,51 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
         lossmask = 0xFu;
       }
       const unsigned ownmask = colmask & rowmask;
-      // ---- phase A: interpolation of the four quadrants, branch-free so that the four chains interleave ----
-      Quad tin, out;
+      // The quadrants are processed kIlp at a time: phase A (interpolation, branch-free so that the kIlp chains
+      // interleave in the FP64 pipe), then phase B (rates of the owned, unstopped cells) for the same quadrants.
+      Quad out;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // cinterp, column_density.f90:108-171, with a common denominator; weightf = 1/max(0.6, tau), :276-293
-        const double m1 = sel_max(t1.v[j], 0.6), m2 = sel_max(t2.v[j], 0.6);
-        const double m3 = sel_max(t3.v[j], 0.6), m4 = sel_max(t4.v[j], 0.6);
-        const double p12 = m1 * m2, p34 = m3 * m4;
-        const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
-        const double num = fma(t1.v[j], e1, fma(t2.v[j], e2, fma(t3.v[j], e3, t4.v[j] * e4)));
-        const double den = (e1 + e2) + (e3 + e4);
-        double tau_in = num * fast_rcp(den);
-        if (kR1) tau_in *= corr;
-        if (kLls == 2) {
-          const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
-          tau_in = fma((double)P.lls_grid[xfast_index(P, F.p, cell)] * P.sigma_HI, pathc, tau_in);
-        } else if (kLls == 1) {
-          tau_in = fma(P.tau_lls, pathc, tau_in);
+      for (int j0 = 0; j0 < 4; j0 += kIlp) {
+        double tin[kIlp];
+#pragma unroll
+        for (int jj = 0; jj < kIlp; ++jj) {
+          const int j = j0 + jj;
+          // cinterp, column_density.f90:108-171, with a common denominator; weightf = 1/max(0.6, tau), :276-293
+          const double m1 = sel_max(t1.v[j], 0.6), m2 = sel_max(t2.v[j], 0.6);
+          const double m3 = sel_max(t3.v[j], 0.6), m4 = sel_max(t4.v[j], 0.6);
+          const double p12 = m1 * m2, p34 = m3 * m4;
+          const double e1 = s1 * (m2 * p34), e2 = s2 * (m1 * p34), e3 = s3 * (m4 * p12), e4 = s4 * (m3 * p12);
+          const double num = fma(t1.v[j], e1, fma(t2.v[j], e2, fma(t3.v[j], e3, t4.v[j] * e4)));
+          const double den = (e1 + e2) + (e3 + e4);
+          double tau_in = num * fast_rcp(den);
+          if (kR1) tau_in *= corr;
+          if (kLls == 2) {
+            const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
+            tau_in = fma((double)P.lls_grid[xfast_index(P, F.p, cell)] * P.sigma_HI, pathc, tau_in);
+          } else if (kLls == 1) {
+            tau_in = fma(P.tau_lls, pathc, tau_in);
+          }
+          tin[jj] = tau_in;
+          out.v[j] = fma(tc.v[j], pathc, tau_in);       // evolve_point.F90:247-248
+          min_hi = min(min_hi, __double2hiint(out.v[j]));
         }
-        tin.v[j] = tau_in;
-        out.v[j] = fma(tc.v[j], pathc, tau_in);       // evolve_point.F90:247-248
-      }
-      // ---- phase B: rates of the cells this face owns and that are not behind the 2e19 column (:201) ------
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if ((ownmask >> j) & 1u) {
-          const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
-          if (kDebug) P.coldens_dbg[xfast_index(P, F.p, cell)] = out.v[j] * P.inv_sigma;
-          if (!(tin.v[j] > P.tau_stop) && !stop_all) {
-            const double tau_cell = tc.v[j];
-            double phi_all, phi_out;
-            photo_rates(tin.v[j], out.v[j], S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
-            // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI)
-            const double inv_vol = fast_rcp(volk * tau_cell);
-            const double photo_cell = phi_all * inv_vol;            // :262
-            if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);   // :283-284
-            // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
-            if ((lossmask >> j) & 1u) loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
+        for (int jj = 0; jj < kIlp; ++jj) {
+          const int j = j0 + jj;
+          if ((ownmask >> j) & 1u) {
+            const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
+            if (kDebug) P.coldens_dbg[xfast_index(P, F.p, cell)] = out.v[j] * P.inv_sigma;
+            if (!(tin[jj] > P.tau_stop) && !stop_all) {    // evolve_point.F90:201
+              const double tau_cell = tc.v[j];
+              double phi_all, phi_out;
+              photo_rates(tin[jj], out.v[j], S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
+              // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI)
+              const double inv_vol = fast_rcp(volk * tau_cell);
+              const double photo_cell = phi_all * inv_vol;            // :262
+              if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);   // :283-284
+              // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
+              if ((lossmask >> j) & 1u) loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
+            }
           }
         }
       }
@@ -416,27 +452,38 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
   __shared__ double s_slot[2][8];                   // per-face boundary loss, alternating by pass (rank 0's copy is used)
   __shared__ int s_work;
 
+  constexpr int kFpg = (kCluster == 1) ? kFpgCta : 1;   // faces per group
+  constexpr int kTg = (kCluster == 1) ? kTgCta : kT;    // threads per group
+  constexpr int kGroups = kNf / kFpg;
+  __shared__ int s_gmin[kGroups][3];                // dead-face rule: smallest high word per group, rotating by shell
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int g = tid / kTg;                          // face group of this thread
+  const int gtid = tid - g * kTg;
+  const int fl = g * kFpg;                          // first face (local to this CTA) of the group
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned crank = (kCluster > 1) ? cluster.block_rank() : 0u;
-  const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;   // one shared plane buffer
+  const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;   // one shared plane buffer of one face
   for (int i = tid; i < kTableLen; i += kT) s_thick[i] = P.thick2[i];
   for (int i = tid; i < 128; i += kT) s_logtab[i] = P.logtab[i];
-  for (int i = tid; i < 2 * (cap + kPadFront); i += kT) s_planes[i] = 0.0;
-  double* sbuf0 = s_planes + kPadFront;
+  for (int i = tid; i < 2 * kNf * (cap + kPadFront); i += kT) s_planes[i] = 0.0;
+  // every face owns two fixed plane buffers (faces run decoupled, so their storage must not move with r):
+  // `cap` doubles each in shared memory, Gf each in the global scratch slot of the work group
+  double* sbuf0 = s_planes + (size_t)(2 * fl) * (cap + kPadFront) + kPadFront;
   double* sbuf1 = sbuf0 + cap + kPadFront;
-  // global plane buffers: a slot of 2*6*Gf doubles per work group, Gf = one face
   const size_t Gf = raytrace_face_doubles(P.plane_stride);
-  double* gbuf0;
-  if (kCluster == 1) gbuf0 = P.scratch + (size_t)blockIdx.x * 2 * kFaces * Gf + kPadFront;
-  else gbuf0 = P.scratch + ((size_t)(blockIdx.x / kCluster) * 2 * kFaces + 2 * crank) * Gf + kPadFront;
-  double* gbuf1 = gbuf0 + kNf * Gf;
+  const size_t slot = (kCluster == 1) ? (size_t)blockIdx.x : (size_t)(blockIdx.x / kCluster);
+  double* gbuf0 = P.scratch + (slot * 2 * kFaces + 2 * ((size_t)crank * kNf + fl)) * Gf + kPadFront;
+  double* gbuf1 = gbuf0 + Gf;
+  const int sstride = 2 * (cap + kPadFront), gstride = (int)(2 * Gf);   // from a face's buffers to the next face's
   LogC L;
   L.c0 = P.logc[0]; L.c1 = P.logc[1]; L.c2 = P.logc[2]; L.c3 = P.logc[3]; L.c4 = P.logc[4]; L.B = P.logB;
   SrcCtx S;
   S.rsafe = min(min(min(P.lim[0][0], P.lim[0][1]), min(P.lim[1][0], P.lim[1][1])), min(P.lim[2][0], P.lim[2][1]));
   int pass_parity = 0;
+  // high word of a column safely above sigma*2e19: a plane whose every high word exceeds it is dead
+  const int dead_hi = __double2hiint(P.tau_stop * 1.000001) + 1;
+  if (tid < kGroups * 3) (&s_gmin[0][0])[tid] = 0x7fffffff;
 
   for (;;) {
     // ---- next source (device-side do_grid_master: one ticket per work group) ---------------------
@@ -460,6 +507,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
     double photon_loss_src = total_source_flux;  // :121
     int lr0 = 0, lr1 = 0, lr2 = 0, ll0 = 0, ll1 = 0, ll2 = 0;  // last_r-src, src-last_l per axis
     int r_done = -1;
+    bool face_dead = false;
     // do while (evolve_source.F90:128-131); every thread of the work group evaluates it on identical values
     while (photon_loss_src > P.loss_fraction * total_source_flux && lr2 < P.lim[2][1] && ll2 < P.lim[2][0]) {
       nbox += 1;
@@ -504,7 +552,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
           const unsigned cell = ((unsigned)src2 * (unsigned)P.n[1] + (unsigned)src1) * (unsigned)P.n[0] + (unsigned)src0;
           const double tau_cell = P.tau_cell[cell];
           const double tau_out = 0.5 * tau_cell;
-          sbuf0[tid] = tau_out;   // plane 0 always fits in shared memory
+          s_planes[(size_t)(2 * (tid >> 2)) * (cap + kPadFront) + kPadFront + (tid & 3)] = tau_out;   // plane 0 of face tid/4, quadrant tid%4
           if (crank == 0 && tid == 0) {
             if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
             if (S.normflux > 0.0) {
@@ -519,34 +567,54 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
         r_done = 0;
       }
       __syncthreads();   // s_face and plane 0 visible
+      // Faces never exchange data (a cell reads the previous plane of its own quadrant only), so the kWpf warps of
+      // a face walk its shells on their own and the work group meets again only for the loss of the pass.
       for (int r = r_done + 1; r <= rmax; ++r) {
-        const int P1 = r + 1;
-        const int nseg = (kCluster == 1) ? P.nseg_cta[r] : P.nseg_cl[r];   // host-tuned split of the columns along b
-        // a plane of side s fits a shared buffer together with the slack the zero-weight reads may touch
-        const bool cur_sm = 4 * kNf * P1 * P1 + 4 * P1 + 8 <= cap;
-        bool prev_sm = 4 * kNf * r * r + 4 * r + 8 <= cap;
-        if (cur_sm) {
-          double* cur = (r & 1) ? sbuf1 : sbuf0;
-          const double* prev = (r & 1) ? sbuf0 : sbuf1;
-          if (r == 1) trace_shell<kNf, false, false, true, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
-          else if (r < S.rsafe) trace_shell<kNf, false, false, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
-          else trace_shell<kNf, false, true, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, prev, cur, nseg, loss);
-        } else {
-          double* cur = (r & 1) ? gbuf1 : gbuf0;
-          double* gprev = (r & 1) ? gbuf0 : gbuf1;
-          if (prev_sm) {
-            // first shell that does not fit: move plane r-1 to the global scratch
-            const double* sprev = (r & 1) ? sbuf0 : sbuf1;
-            const int nmove = 4 * kNf * r * r;
-            for (int i = tid; i < nmove; i += kT) gprev[i] = sprev[i];
-            __syncthreads();
-            prev_sm = false;
+        int min_hi = 0x7fffffff;   // high word of the smallest optical depth this thread writes to plane r
+        if (!face_dead) {
+          const int P1 = r + 1;
+          const int nseg = (kCluster == 1) ? P.nseg_cta[r] : P.nseg_cl[r];   // host-tuned split of the columns along b
+          // a plane of side s fits a shared buffer together with the slack the zero-weight reads may touch
+          const bool cur_sm = 4 * P1 * P1 + 4 * P1 + 8 <= cap;
+          const bool prev_sm = 4 * r * r + 4 * r + 8 <= cap;
+          const Face* faces = s_face + fl;
+          if (cur_sm) {
+            double* cur = (r & 1) ? sbuf1 : sbuf0;
+            const double* prev = (r & 1) ? sbuf0 : sbuf1;
+            if (r == 1) trace_shell<kFpg, kTg, false, false, true, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, false, false, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            else trace_shell<kFpg, kTg, false, true, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
+          } else {
+            double* cur = (r & 1) ? gbuf1 : gbuf0;
+            double* gprev = (r & 1) ? gbuf0 : gbuf1;
+            if (prev_sm) {
+              // first shell that does not fit: the group moves its planes r-1 to the global scratch
+              const double* sprev = (r & 1) ? sbuf0 : sbuf1;
+              for (int f = 0; f < kFpg; ++f)
+                for (int i = gtid; i < 4 * r * r; i += kTg) gprev[f * gstride + i] = sprev[f * sstride + i];
+              group_sync<kTg>(g);
+            }
+            if (r == 1) trace_shell<kFpg, kTg, true, false, true, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, true, false, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            else trace_shell<kFpg, kTg, true, true, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
           }
-          if (r == 1) trace_shell<kNf, true, false, true, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
-          else if (r < S.rsafe) trace_shell<kNf, true, false, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
-          else trace_shell<kNf, true, true, false, kLls, kDebug>(P, S, s_face, s_thick, s_logtab, L, r, gprev, cur, nseg, loss);
         }
-        __syncthreads();   // plane r complete before plane r+1 reads it (quadrants never cross CTAs)
+        // plane r complete before plane r+1 reads it.  Dead-face rule: once every optical depth of the planes of a
+        // group exceeds the 2e19 column (evolve_point.F90:201) by a margin, every later cell of these faces
+        // interpolates to more than the limit as well (a weighted mean of such values, plus non-negative terms):
+        // no rate, no boundary loss, so the group skips the arithmetic of its remaining shells (the cells still
+        // count as updates).
+        const int wmin = __reduce_min_sync(0xffffffffu, min_hi);
+        if (kTg == 32) {
+          __syncwarp();
+          if (!kDebug && !face_dead) face_dead = wmin > dead_hi;
+        } else {
+          const int slot3 = r % 3;
+          if (lane == 0 && !face_dead) atomicMin(&s_gmin[g][slot3], wmin);
+          group_sync<kTg>(g);
+          if (!kDebug && !face_dead) face_dead = s_gmin[g][slot3] > dead_hi;
+          if (gtid == 0) s_gmin[g][(r + 2) % 3] = 0x7fffffff;   // the slot of shell r+2: nobody touches it before the barrier of r+1
+        }
       }
       r_done = rmax;
       // photon_loss_src = sum over the work group (plays photon_loss_src_thread, evolve_source.F90:183-186)
@@ -607,8 +675,9 @@ size_t raytrace_scratch_doubles_per_cta(int plane_stride) {
   return (size_t)2 * kFaces * raytrace_face_doubles(plane_stride);
 }
 
-static size_t rt_smem_bytes(int plane_doubles) {
-  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * (plane_doubles + kPadFront) * sizeof(double);
+// plane_doubles = capacity of one plane buffer of one face; a CTA holds two per face
+static size_t rt_smem_bytes(int plane_doubles, int nfaces) {
+  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * nfaces * (plane_doubles + kPadFront) * sizeof(double);
 }
 
 typedef void (*RtKernel)(RtParams);
@@ -650,32 +719,31 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2) + 2 * kPadFront * sizeof(double);
-  // kCtaPerSm CTAs per SM share the opt-in shared memory; what the tables leave goes to the two plane buffers
-  int per_cta = std::min(max_optin, sm_total / kCtaPerSm - 2048);
-  if (const char* env = getenv("C2B_RT_SMEM_KB")) per_cta = std::min(per_cta, atoi(env) * 1024);
-  int cap = (int)(((size_t)per_cta - fixed - 1024) / (2 * sizeof(double)));
-  const int full = 4 * kFaces * (max_radius + 1) * (max_radius + 1);
-  const int slack = 4 * (max_radius + 1) + 8;
-  const int cap_cta = std::max(128, std::min(cap, full + slack)) & ~3;
-  const int cap_cl = std::max(128, std::min(cap, full / kClusterSize + slack)) & ~3;
+  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
+  // kCtaPerSm CTAs per SM share the opt-in shared memory; what the tables leave goes to the plane buffers
+  int per_cta = std::min(std::min(max_optin, sm_total / kCtaPerSm - 2048), 56 * 1024);   // the rest of the SM's 256 KB is L1 for the global planes
+  if (const char* env = getenv("C2B_RT_SMEM_KB")) per_cta = std::min(std::min(max_optin, sm_total / kCtaPerSm - 2048), atoi(env) * 1024);
+  const int avail = (int)(((size_t)per_cta - fixed - 1024) / sizeof(double));   // doubles for all plane buffers of a CTA
+  const int full = 4 * (max_radius + 1) * (max_radius + 1) + 4 * (max_radius + 1) + 8;   // one face at the largest radius
+  const int cap_cta = std::max(64, std::min(avail / (2 * kFaces) - kPadFront, full)) & ~3;
+  const int cap_cl = std::max(64, std::min(avail / 2 - kPadFront, full)) & ~3;
   for (int dbg = 0; dbg < 2; ++dbg)
     for (int lls = 1; lls < 4; ++lls) {
       cudaError_t e = cudaFuncSetAttribute(pick_kernel<1>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)rt_smem_bytes(cap_cta));
+                                           (int)rt_smem_bytes(cap_cta, kFaces));
       if (e != cudaSuccess) return (int)e;
       e = cudaFuncSetAttribute(pick_kernel<kClusterSize>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)rt_smem_bytes(cap_cl));
+                               (int)rt_smem_bytes(cap_cl, 1));
       if (e != cudaSuccess) return (int)e;
     }
   info->smem_plane_doubles = cap_cta;
   info->smem_plane_doubles_cl = cap_cl;
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<1>(1, false), kT, rt_smem_bytes(cap_cta));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<1>(1, false), kT, rt_smem_bytes(cap_cta, kFaces));
   info->grid_cta = sms * std::max(1, per_sm);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, sms, rt_smem_bytes(cap_cl), nullptr);
+  cluster_config(&cfg, attr, sms, rt_smem_bytes(cap_cl, 1), nullptr);
   int nclusters = 0;
   cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, pick_kernel<kClusterSize>(1, false), &cfg);
   if (e != cudaSuccess) return (int)e;
@@ -686,8 +754,8 @@ int raytrace_configure(int max_radius, RtLaunchInfo* info) {
   return 0;
 }
 
-// Number of b-segments per column for shell r: minimises rounds x (segment length + set-up) for a CTA
-// that owns `nf` faces, i.e. nf*(r+1) columns of four cells per row.
+// Number of b-segments per column for shell r: minimises rounds x (segment length + set-up) for the `threads`
+// threads that walk a group of `nf` faces, i.e. nf*(r+1) columns of four cells per row.
 static void build_nseg_table(int max_radius, int nf, int threads, std::vector<int>& tab) {
   tab.assign((size_t)max_radius + 2, 1);
   for (int r = 1; r <= max_radius; ++r) {
@@ -704,20 +772,20 @@ static void build_nseg_table(int max_radius, int nf, int threads, std::vector<in
 }
 
 void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl) {
-  build_nseg_table(max_radius, kFaces, kT, cta);
-  build_nseg_table(max_radius, 1, kT, cl);
+  build_nseg_table(max_radius, kFpgCta, kTgCta, cta);   // single-CTA kernel: groups of kFpgCta faces
+  build_nseg_table(max_radius, 1, kT, cl);              // cluster kernel: the whole CTA walks one face
 }
 
 static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles), stream>>>(p);
+  pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles, kFaces), stream>>>(p);
 }
 
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl), stream);
+  cluster_config(&cfg, attr, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl, 1), stream);
   return (int)cudaLaunchKernelEx(&cfg, pick_kernel<kClusterSize>(lls_mode(p), p.coldens_dbg != nullptr), p);
 }
 

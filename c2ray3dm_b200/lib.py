@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libc2ray_b200.so")
+LIB_PATH = os.environ.get("C2B_LIB") or os.path.join(HERE, "libc2ray_b200.so")   # C2B_LIB: development builds (scripts/build_variant.sh)
 
 NUMTAU = 2000
 MAX_ITER = 104
