@@ -10,10 +10,14 @@ iterations of {ray-trace every source, reduce the rate grid over ranks, per-cell
 
 Workload (N=1): BASELINE.json configs[2] -- synthetic log-normal density 256^3, 10^4 sources at the
 density peaks, clumping grid on, LLS on, mid-reionization bubble state (mean ionized fraction 0.54: spheres of up to
-25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  With --gpus N the source list grows to N x 10^4 (weak scaling) and the bubble
-radius shrinks by N^(-1/3) so that the ionized volume, and with it the work per GPU, stays comparable: every
-GPU holds the full grids and traces its round-robin share (master_slave.F90:85), the partial rate grids are
-summed with ncclAllReduce (evolve.F90:599-602).
+25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  Every step is one
+evolve3D(dt) call from the SAME snapshot (S1), restored on the device before the call, so the time per step is
+stationary; the early-reionization state S0 (xh = 2e-4) is measured beside it (key "S0").  With --gpus N the source
+list grows to N x 10^4 (weak scaling) and the bubble radius shrinks by N^(-1/3) so that the ionized volume, and with it
+the work per GPU, stays comparable (--scaling strong keeps --nsrc sources in total): every GPU holds the full grids
+and traces its round-robin share (master_slave.F90:85), the partial rate grids are summed with ncclAllReduce
+(evolve.F90:599-602).  After the timed legs the sampled-source rate grid of the cpu_baseline leg is compared with
+the GPU's ("parity_rel_err", must be <= 1e-6).
 
 The reference is Fortran and cannot be built in this image (no Fortran compiler), so the reference arm
 and cpu_baseline time the C restatement in oracle/ ("kind": "port") on the host cores.
@@ -35,9 +39,14 @@ METRIC = "cell-source raytrace updates/s"
 UNIT = "updates/s"
 B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 + xh_av 8 + phih RMW 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one raytrace_kernel launch on this workload divided by
-# the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r1_summary.txt)
-NCU_DRAM_BYTES_PER_UPDATE = 21.6
-FP64_INSTR_PER_UPDATE = 91  # FP64-pipe instructions in the inner loop of raytrace_kernel (static SASS, scripts/sass_loop.py)
+# the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r2_summary.txt)
+NCU_DRAM_BYTES_PER_UPDATE = 19.9
+# the same capture (profiles/ncu_raytrace_r2_summary.txt): measured counters, not static instruction counts
+NCU_SOURCE = "profiles/ncu_raytrace_r2_summary.txt"
+NCU_DRAM_PCT = 33.7         # gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
+NCU_FP64_PCT = 43.5         # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+NCU_ISSUE_PCT = 50.3        # smsp__issue_active.avg.pct_of_peak_sustained_active
+NCU_INSTR_PER_UPDATE = 4.2  # smsp__inst_executed.sum / updates of the launch
 YEAR = 3.15576e7
 
 
@@ -54,6 +63,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="sources in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-s0", action="store_true", help="skip the early-reionization (S0) extra measurement")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --nsrc sources per GPU (default); strong: --nsrc sources in total")
     return ap.parse_args()
 
 
@@ -116,10 +128,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_sample(w, mesh, nsample, threads):
+def cpu_sample(w, mesh, nsample, threads, keep=False):
     """times the C restatement (oracle/) on a bounded sample: one pass over every k-th source + one
     per-cell pass, on `threads` host threads (sources dealt to threads, private rate grids summed: the
-    reference's MPI picture).  Returns (updates/s, description, seconds)."""
+    reference's MPI picture).  Returns (updates/s, description, seconds, updates[, source selection, rate grid])."""
     from oracle import oracle as O
     ns = len(w["normflux"])
     stride = max(1, ns // max(1, nsample))
@@ -139,11 +151,14 @@ def cpu_sample(w, mesh, nsample, threads):
     t0 = time.perf_counter()
     r = o.pass_all_sources()
     t1 = time.perf_counter()
+    phih = o.phih.copy() if keep else None
     o.global_pass(0.5e6 * YEAR, r.photon_loss_all)
     t2 = time.perf_counter()
     desc = ("%d of %d sources (every %dth, file order) of the %d^3 workload: 1 pass_all_sources (%.2fs) + "
-            "1 global_pass (%.2fs), C restatement, %d threads source-parallel" % (
-                len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads))
+            "1 global_pass (%.2fs), C restatement, %d threads, mode: source-parallel (one source per thread, private "
+            "rate grids summed: do_grid_static + MPI_ALLREDUCE)" % (len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads))
+    if keep:
+        return r.updates / (t1 - t0), desc, t2 - t0, r.updates, sel, phih
     return r.updates / (t1 - t0), desc, t2 - t0, r.updates
 
 
@@ -152,7 +167,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    w = build_workload(args.mesh, args.nsrc * args.gpus, args.bubble * args.gpus ** (-1.0 / 3.0))
+    strong = args.scaling == "strong"
+    w = build_workload(args.mesh, args.nsrc if strong else args.nsrc * args.gpus,
+                       args.bubble if strong else args.bubble * args.gpus ** (-1.0 / 3.0))
     nsample = args.cpu_sample or max(cores * 4, 64)
     rates, secs, upd = [], [], []
     desc = ""
@@ -169,7 +186,7 @@ def run_reference(args):
     value = float(np.sum(upd) / np.sum([u / r for u, r in zip(upd, rates)]))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,16 +196,25 @@ def run_reference(args):
     return 0
 
 
-def workload_config(args):
-    return {"workload": "synthetic lognormal density %d^3, %d sources/GPU at density peaks, clumping grid (type 5), "
-                        "LLS type 1, mid-reionization bubble state r<=%.1f cells, z=9, dt=%g Myr (BASELINE configs[2])" % (
-                            args.mesh, args.nsrc, args.bubble * args.gpus ** (-1.0 / 3.0), args.dt_myr),
-            "mesh": args.mesh, "sources_total": args.nsrc * args.gpus, "parallelism": "source-sharded x%d" % args.gpus,
-            "l2": "grids (ndens+xh_av+phih = %.0f MB) exceed the 126 MB L2" % (20 * args.mesh ** 3 / 1e6)
+def workload_config(args, world=None):
+    world = world or args.gpus
+    strong = args.scaling == "strong"
+    total = args.nsrc if strong else args.nsrc * world
+    bubble = args.bubble if strong else args.bubble * world ** (-1.0 / 3.0)
+    return {"workload": "synthetic lognormal density %d^3, %d sources in total (%s) at density peaks, clumping grid "
+                        "(type 5), LLS type 1, z=9, dt=%g Myr; every step = one evolve3D call from the same "
+                        "mid-reionization snapshot S1 (bubbles r<=%.1f cells, mean x=0.54 at 1 GPU), restored on the "
+                        "device before the call (BASELINE configs[%d])" % (
+                            args.mesh, total, "%d per GPU" % args.nsrc if not strong else "strong scaling", args.dt_myr,
+                            bubble, 3 if args.mesh == 512 else 2),
+            "mesh": args.mesh, "sources_total": total, "parallelism": "source-sharded x%d" % world,
+            "state": "S1 restored every step (stationary)",
+            "l2": "grids (tau_cell + twin + phih + twin = %.0f MB) exceed the 126 MB L2" % (32 * args.mesh ** 3 / 1e6)
             if args.mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
 
 
 def run_ours(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     from c2ray3dm_b200 import Evolve
@@ -205,7 +231,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mesh = args.mesh
-    w = build_workload(mesh, args.nsrc * world, args.bubble * world ** (-1.0 / 3.0))
+    strong = args.scaling == "strong"
+    nsrc_total = args.nsrc if strong else args.nsrc * world
+    bubble = args.bubble if strong else args.bubble * world ** (-1.0 / 3.0)
+    w = build_workload(mesh, nsrc_total, bubble)
     dt = args.dt_myr * 1e6 * YEAR
 
     e = Evolve(mesh, device=local, rank=rank, nranks=world, type_of_clumping=5, use_LLS=True, type_of_LLS=1)
@@ -223,6 +252,7 @@ def run_ours(args):
     xh_pin = torch.from_numpy(w["xh"].reshape(-1).copy()).pin_memory()
     e.set_density(nd_pin.numpy())
     e.set_xh(xh_pin.numpy())
+    e.save_xh()      # the S1 snapshot every step starts from (device-resident)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,11 +268,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # Every step is one evolve3D(dt) call from the SAME mid-reionization snapshot S1, restored on the device
+    # (134 MB device-to-device at 256^3, ~0.1 ms, inside the timed region), so ms_per_step is stationary and
+    # comparable across N and rounds.
     tsim = 0.0
-    reports = []
     for _ in range(args.warmup):
-        reports.append(e.evolve3D(tsim, dt))
-        tsim += dt
+        e.restore_xh()
+        e.evolve3D(tsim, dt)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -252,43 +284,68 @@ def run_ours(args):
     upd = launches = 0
     ms_rt = ms_chem = ms_ar = ms_dev = 0.0
     niter = 0
+    step_ms = []
     for _ in range(args.steps):
+        e.restore_xh()
         rep = e.evolve3D(tsim, dt)
-        tsim += dt
         upd += rep.total_updates
         launches += rep.kernel_launches
         ms_rt += rep.ms_raytrace
         ms_chem += rep.ms_chemistry
         ms_ar += rep.ms_allreduce
         ms_dev += rep.ms_total
+        step_ms.append(rep.ms_total)
         niter += rep.niter
     barrier()
     wall = maxreduce(time.perf_counter() - t0)
     ms_rt_max = maxreduce(ms_rt)
     # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------
+    # what fortran/evolve_b200.F90 moves per evolve3D call: ndens + xh in, xh + phih_grid out
     e2e = None
+    dptr = ctypes.POINTER(ctypes.c_double)
     if not args.no_e2e:
         xh_out = torch.empty(mesh ** 3, dtype=torch.float64).pin_memory()
-        xh_pin.copy_(torch.from_numpy(e.xh.reshape(-1)))   # continue from the evolved state (untimed)
+        ph_out = torch.empty(mesh ** 3, dtype=torch.float64).pin_memory()
         barrier()
         t0 = time.perf_counter()
         upd2 = 0
         for _ in range(args.steps):
             e.set_density(nd_pin.numpy())     # what the host re-sends after cosmo_evol (cosmology.F90:186)
-            e.set_xh(xh_pin.numpy())          # ionfractions_module.F90:22
+            e.set_xh(xh_pin.numpy())          # ionfractions_module.F90:22 (the S1 snapshot again)
             rep = e.evolve3D(tsim, dt)
-            xh_np = xh_out.numpy()
-            e._ck(e.L.c2b_get_xh(e.h, xh_np.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_double))), "c2b_get_xh")
-            xh_pin.copy_(xh_out)              # next step starts from the returned state, as the host would
-            tsim += dt
+            e._ck(e.L.c2b_get_xh(e.h, xh_out.numpy().ctypes.data_as(dptr)), "c2b_get_xh")
+            e._ck(e.L.c2b_get_phih(e.h, ph_out.numpy().ctypes.data_as(dptr)), "c2b_get_phih")
             upd2 += rep.total_updates
         barrier()
         wall2 = maxreduce(time.perf_counter() - t0)
         e2e = {"value": upd2 / wall2, "unit": UNIT, "h2d_bytes_per_step": 12 * mesh ** 3,
-               "d2h_bytes_per_step": 8 * mesh ** 3, "ms_per_step": 1e3 * wall2 / args.steps}
+               "d2h_bytes_per_step": 16 * mesh ** 3, "ms_per_step": 1e3 * wall2 / args.steps}
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
+    # ---- early-reionization state S0: xh = 2e-4 everywhere, every trace ends in subbox 1-3 ------
+    s0 = None
+    if not args.no_s0:
+        from c2ray3dm_b200 import constants as K
+        xh0 = torch.full((mesh ** 3,), K.xh_initial, dtype=torch.float64).pin_memory()
+        u0 = rt0 = 0.0
+        t_s0 = 0.0
+        for i in range(3):
+            e.set_xh(xh0.numpy())
+            barrier()
+            t0 = time.perf_counter()
+            rep = e.evolve3D(tsim, dt)
+            barrier()
+            if i > 0:   # the first step is the warm-up (it also re-learns the per-source trace lengths)
+                t_s0 += maxreduce(time.perf_counter() - t0)
+                u0 += rep.total_updates
+                rt0 += rep.ms_raytrace
+        rt0 = maxreduce(rt0)
+        s0 = {"state": "S0: xh = 2e-4 everywhere (every trace ends in subbox 1-3)", "value": u0 / t_s0, "unit": UNIT,
+              "ms_per_step": 1e3 * t_s0 / 2, "updates_per_step": u0 / 2,
+              "raytrace_updates_per_s_per_gpu": (u0 / world) / (rt0 * 1e-3) if rt0 > 0 else None,
+              "raytrace_frac_of_hbm_roofline": (u0 / world) * B_RT / (rt0 * 1e-3) / 1e9 / load_peaks()[0] if rt0 > 0 else None}
+        e.set_xh(xh_pin.numpy())
     peak, peak_kind = load_peaks()
     dfma = e.measure_dfma_rate()
     line = None
@@ -298,9 +355,10 @@ def run_ours(args):
         achieved = upd_rank * B_RT / (ms_rt_max * 1e-3) / 1e9 if ms_rt_max > 0 else 0.0
         line = {"metric": METRIC, "value": upd / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args),
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world),
                 "seconds_per_evolve3D_step": wall / args.steps,
+                "step_ms": step_ms,
                 "updates_per_step": upd / args.steps, "outer_iterations_per_step": niter / args.steps,
                 "gpu_launches": int(launches),
                 "phase_ms_per_step": {"raytrace": ms_rt / args.steps, "allreduce": ms_ar / args.steps,
@@ -313,21 +371,39 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": B_RT * upd_rank / max(1, niter),
                              "peak_source": "%s (MEASURED_PEAKS.json hbm_gbs)" % peak_kind,
                              "algorithmic_bytes_per_update": B_RT,
-                             "note": "FP64-issue bound expected to bind first (SURVEY 8d)"},
-                "fp64": {"dfma_per_s_measured": dfma, "fp64_instr_per_update_sass": FP64_INSTR_PER_UPDATE,
-                         "updates_per_s_per_gpu_raytrace": upd_rank / (ms_rt_max * 1e-3) if ms_rt_max > 0 else 0.0,
-                         "frac_of_fp64_issue_bound": (upd_rank / (ms_rt_max * 1e-3)) * FP64_INSTR_PER_UPDATE / dfma
-                         if ms_rt_max > 0 and dfma > 0 else None},
+                             "note": "the kernel is issue/latency-bound, not bandwidth-bound (profiles/): DRAM "
+                                     "throughput and FP64-pipe activity measured by ncu are in `ncu`"},
+                "ncu": {"source": NCU_SOURCE, "dram_throughput_pct": NCU_DRAM_PCT, "fp64_pipe_active_pct": NCU_FP64_PCT,
+                        "issue_active_pct": NCU_ISSUE_PCT, "warp_instr_per_update": NCU_INSTR_PER_UPDATE,
+                        "dfma_per_s_probe": dfma},
                 "clocks": sampler.summary(),
+                "S0": s0,
                 "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         nsample = args.cpu_sample or max(cores * 4, 64)
-        v, desc, s, u = cpu_sample(w, mesh, nsample, cores)
+        v, desc, s, u, sel, ph_cpu = cpu_sample(w, mesh, nsample, cores, keep=True)
         if s < 5:  # scale the sample towards ~10-30 s of CPU work
             nsample = min(len(w["normflux"]), int(nsample * 15 / max(s, 1e-3)))
-            v, desc, s, u = cpu_sample(w, mesh, nsample, cores)
+            v, desc, s, u, sel, ph_cpu = cpu_sample(w, mesh, nsample, cores, keep=True)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        # parity of the timed workload: the same sampled sources, one pass from the S1 snapshot, GPU vs CPU
+        e.set_sources(w["srcpos"][sel], w["normflux"][sel])
+        e.set_xh(xh_pin.numpy())
+        e.begin_step()
+        g = e.pass_all_sources()
+        ph_gpu = e.phih_grid.reshape(-1)
+        ph_cpu = ph_cpu.reshape(-1)
+        nz = ph_cpu != 0
+        err = float(np.max(np.abs(ph_gpu[nz] - ph_cpu[nz]) / ph_cpu[nz]))
+        line["parity_rel_err"] = err
+        line["parity"] = {"what": "phih_grid of the cpu_baseline sample (%d sources, one pass from S1): max relative "
+                                  "difference GPU vs CPU restatement; update counts equal: %s; cells with a rate equal: %s"
+                                  % (len(sel), g.updates == u, bool(np.array_equal(ph_gpu != 0, nz))),
+                          "tolerance": 1e-6, "ok": bool(err <= 1e-6 and g.updates == u and np.array_equal(ph_gpu != 0, nz))}
+        if not line["parity"]["ok"]:
+            print(json.dumps(line))
+            raise SystemExit("bench.py: the timed workload does not match the CPU restatement (parity_rel_err %.3e)" % err)
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -67,6 +67,7 @@ struct c2b_handle {
   float *d_clump = nullptr, *d_lls = nullptr, *d_f32tmp = nullptr;
   double *d_thick = nullptr, *d_thin = nullptr, *d_taucell = nullptr;
   double *d_taucell_t = nullptr, *d_phih_t = nullptr;   // y-fastest twins for the x-principal quadrants
+  double* d_xh_saved = nullptr;                         // c2b_save_xh_dev
   bool taucell_t_dirty = true;
   double2 *d_thick2 = nullptr, *d_logtab = nullptr;
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
@@ -332,6 +333,7 @@ void c2b_destroy(c2b_handle* h) {
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
   cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_taucell_t); cudaFree(h->d_phih_t); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
   cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
+  cudaFree(h->d_xh_saved);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -1096,6 +1098,25 @@ void* c2b_dev_ptr(c2b_handle* h, const char* name) {
   if (!strcmp(name, "xh_intermed")) return h->d_xh_intermed;
   if (!strcmp(name, "phih")) return h->d_phih;
   return nullptr;
+}
+
+// harness: keeps a device copy of xh so that a benchmark can start every step from the same state
+int c2b_save_xh_dev(c2b_handle* h) {
+  C2B_CHECK_H(h);
+  if (!h->have_xh) return fail(h, "c2b_save_xh_dev: ionization fractions not set");
+  if (bind_device(h)) return 1;
+  if (!h->d_xh_saved) CU(h, cudaMalloc(&h->d_xh_saved, h->ncell * sizeof(double)));
+  CU(h, cudaMemcpyAsync(h->d_xh_saved, h->d_xh, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int c2b_restore_xh_dev(c2b_handle* h) {
+  C2B_CHECK_H(h);
+  if (!h->d_xh_saved) return fail(h, "c2b_restore_xh_dev: nothing saved");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_xh, h->d_xh_saved, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  return 0;
 }
 
 int c2b_synchronize(c2b_handle* h) {

@@ -261,3 +261,10 @@ class Evolve:
 
     def synchronize(self):
         self._ck(self.L.c2b_synchronize(self.h), "c2b_synchronize")
+
+    def save_xh(self):
+        """keeps a device copy of xh (harness: a benchmark restarts every step from it)"""
+        self._ck(self.L.c2b_save_xh_dev(self.h), "c2b_save_xh_dev")
+
+    def restore_xh(self):
+        self._ck(self.L.c2b_restore_xh_dev(self.h), "c2b_restore_xh_dev")

@@ -70,7 +70,7 @@ c2b_set_lls_grid c2b_set_lls_rmax c2b_set_temperature c2b_set_sources c2b_set_xh
 c2b_begin_step c2b_pass_all_sources c2b_global_pass c2b_end_step c2b_get_xh c2b_get_xh_av
 c2b_get_xh_intermed c2b_get_phih c2b_get_phih_f32 c2b_get_source_nbox c2b_get_source_loss
 c2b_get_iter_state c2b_set_iter_state c2b_dev_ptr c2b_synchronize c2b_trace_source_debug
-c2b_measure_dfma_rate""".split()
+c2b_measure_dfma_rate c2b_save_xh_dev c2b_restore_xh_dev""".split()
 
 _lib = None
 
@@ -124,6 +124,8 @@ def load():
     L.c2b_dev_ptr.argtypes = [vp, C.c_char_p]
     L.c2b_dev_ptr.restype = vp
     L.c2b_synchronize.argtypes = [vp]
+    L.c2b_save_xh_dev.argtypes = [vp]
+    L.c2b_restore_xh_dev.argtypes = [vp]
     L.c2b_trace_source_debug.argtypes = [vp, C.c_int32, dp, dp, ip, dp]
     L.c2b_measure_dfma_rate.argtypes = [vp, dp]
     _lib = L

@@ -174,6 +174,9 @@ int c2b_set_iter_state(c2b_handle *h, int32_t niter, double photon_loss_all, con
 /* ---- device-side access for harnesses that already hold data in HBM (bench, tests) -------- */
 void *c2b_dev_ptr(c2b_handle *h, const char *name); /* "ndens","xh","xh_av","xh_intermed","phih" */
 int c2b_synchronize(c2b_handle *h);
+/* keep / bring back a device-resident copy of xh (benchmarks start every step from the same state) */
+int c2b_save_xh_dev(c2b_handle *h);
+int c2b_restore_xh_dev(c2b_handle *h);
 /* single-source diagnostic: traces source ns (1-based) alone into a zeroed phih and returns the
  * full coldensh_out grid the reference would hold after do_source (evolve_source.F90:58-221). */
 int c2b_trace_source_debug(c2b_handle *h, int32_t ns, double *coldensh_out, double *phih_grid,

@@ -792,7 +792,8 @@ void orc_set_rates_to_zero(orc_state *s) {
 void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
   int64_t sum_nbox = 0, updates = 0;
   double photon_loss = 0.0;
-  if (s->nthreads <= 1) {
+  const int mine = (s->NumSrc - s->rank + s->npr - 1) / s->npr; /* sources of this rank */
+  if (s->nthreads <= 1 || mine <= 1) {
     for (int ns1 = 1 + s->rank; ns1 <= s->NumSrc; ns1 += s->npr) {
       orc_source_report r;
       do_source(s, s->coldensh_out, s->phih_grid, ns1, &r);
@@ -801,7 +802,7 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
       updates += r.updates;
     }
   } else {
-    int T = s->nthreads;
+    int T = s->nthreads < mine ? s->nthreads : mine;
     double **priv = (double **)calloc((size_t)T, sizeof(double *));
     double *ploss = (double *)calloc((size_t)T, sizeof(double));
     int64_t *pnbox = (int64_t *)calloc((size_t)T, sizeof(int64_t));
@@ -952,6 +953,8 @@ static void state_after(orc_state *s, const double *xh_l) { /* :190-217 */
 static void total_rates(orc_state *s, double dt, const double *xh_l) { /* :137-185 */
   double totrec = 0.0, totcoll = 0.0;
   const double T = s->temper_val;
+  /* loop invariants evaluated once; every product below keeps the reference's left-to-right order */
+  const double powT = pow(T / F32(1e4f), K_albpow), sqrtT = sqrt(T), expT = exp(-K_temph0() / T);
   for (size_t p = 0; p < s->ncell; ++p) {
     double yh[2];
     yh[0] = 1.0 - xh_l[p];
@@ -960,10 +963,8 @@ static void total_rates(orc_state *s, double dt, const double *xh_l) { /* :137-1
     float clumping = s->clumping;
     if (s->type_of_clumping == 3 || s->type_of_clumping == 4 || s->type_of_clumping == 5)
       clumping = s->clumping_grid[p];
-    totrec = totrec + ndens_p * yh[1] * electrondens(ndens_p, yh) * (double)clumping * K_bh00 *
-                          pow(T / F32(1e4f), K_albpow);
-    totcoll = totcoll + ndens_p * yh[0] * electrondens(ndens_p, yh) * K_colh0() * sqrt(T) *
-                            exp(-K_temph0() / T);
+    totrec = totrec + ndens_p * yh[1] * electrondens(ndens_p, yh) * (double)clumping * K_bh00 * powT;
+    totcoll = totcoll + ndens_p * yh[0] * electrondens(ndens_p, yh) * K_colh0() * sqrtT * expT;
   }
   s->totrec = totrec * s->vol * dt;
   s->totcollisions = totcoll * s->vol * dt;
@@ -1002,7 +1003,11 @@ void orc_global_pass(orc_state *s, double dt, double photon_loss_all, orc_global
   for (size_t p = 1; p < s->ncell; ++p) if (s->xh_av[p] > maxav) maxav = s->xh_av[p];
   rep->min_avg_neutral = F32(1.0f) - maxav; /* :535 */
   int conv_flag = 0;
-  for (size_t p = 0; p < s->ncell; ++p) evolve0D_global(s, dt, p, &conv_flag); /* :548-555, i fastest */
+  /* :548-555, i fastest.  The cells are independent (conv_flag is an integer count), so with
+   * orc_set_threads(n > 1) the loop is shared between host threads; the result is bit-identical. */
+  const long long ncell = (long long)s->ncell;
+#pragma omp parallel for num_threads(s->nthreads) reduction(+ : conv_flag) schedule(static)
+  for (long long p = 0; p < ncell; ++p) evolve0D_global(s, dt, (size_t)p, &conv_flag);
   rep->conv_flag = conv_flag;
   double sum = 0.0;
   for (size_t p = 0; p < s->ncell; ++p) sum = sum + s->xh_intermed[p];

@@ -23,7 +23,7 @@ DT = 1e6 * 3.15576e7
 @pytest.fixture(params=["auto", "cta", "cluster"], autouse=True)
 def routing(request, monkeypatch):
     """every test runs with the default routing of sources to the two ray-trace kernels, with the
-    one-CTA-per-source kernel only, and with the cluster-of-8 kernel only"""
+    one-CTA-per-source kernel only, and with the cluster-of-6 kernel only"""
     if request.param == "cta":
         monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
         monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
@@ -390,29 +390,6 @@ def test_translation_invariance_periodic(gpu_tables):
     np.testing.assert_allclose(roll(a[1]), b[1], rtol=0, atol=1e-9)
 
 
-@pytest.mark.skipif(os.environ.get("C2B_SLOW", "0") != "1", reason="one full-box source on 512^3: set C2B_SLOW=1")
-def test_full_box_update_count_512_quirk():
-    """N=512: R=255=5*51 stops the walk one pass before the -256 layer is reached: 511^3 updates per
-    fully-traced source.  Uses a tiny flux threshold so the trace covers the box."""
-    N = 512
-    import c2ray3dm_b200 as pkg
-    from c2ray3dm_b200 import synthetic as syn
-    e = pkg.Evolve(N, use_LLS=False, loss_fraction=0.0)
-    e.rad_ini()
-    e.set_density(np.full(N ** 3, syn.avg_dens(9.0), dtype=np.float32))
-    dr, vol = syn.proper_geometry(N, 9.0)
-    e.set_geometry(dr, vol)
-    e.set_sources(np.array([[100, 200, 300]], dtype=np.int32), [1e9])
-    e.set_xh(np.full(N ** 3, 1.0 - 1e-6))
-    e.begin_step()
-    r = e.pass_all_sources()
-    assert r.sum_nbox_all == 51
-    assert r.updates == 511 ** 3
-    ph = e.phih_grid
-    assert np.count_nonzero(ph) == 511 ** 3
-    e.close()
-
-
 def test_nbody_test_history_single_source(gpu_tables):
     """BASELINE config 1 in miniature: the nbody_test problem (uniform mean density at z=9, 100/h Mpc box,
     LLS type 1, xh=2e-4, T=1e4 K, one 1e57 s^-1 source), 4 consecutive steps with cosmo_evol between them;
@@ -484,11 +461,9 @@ def test_full_box_trace_spills_planes_to_global(gpu_tables):
     e.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-def test_cluster_kernel_shapes(variant, gpu_tables, monkeypatch):
-    """every compiled shape of the cluster kernel (octant per CTA with one or three warp groups, one or
-    two CTAs per SM, four octants per CTA) gives the oracle's answer"""
-    monkeypatch.setenv("C2B_CLUSTER_VARIANT", str(variant))
+def test_cluster_kernel_full_step(gpu_tables, monkeypatch):
+    """the cluster kernel (six CTAs, one per cube face, boundary loss summed over DSMEM) on every source of a full
+    evolve3D step, and its diagnostic trace, against the oracle"""
     monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "0")
     monkeypatch.setenv("C2B_CLUSTER_MAX_SOURCES", "1000000")
     monkeypatch.setenv("C2B_DEBUG_CLUSTER", "1")
