@@ -13,8 +13,9 @@ density peaks, clumping grid on, LLS on, mid-reionization bubble state (mean ion
 25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  Every step is one
 evolve3D(dt) call from the SAME snapshot (S1), restored on the device before the call, so the time per step is
 stationary; the early-reionization state S0 (xh = 2e-4) is measured beside it (key "S0").  With --gpus N the source
-list grows to N x 10^4 (weak scaling) and the bubble radius shrinks by N^(-1/3) so that the ionized volume, and with it
-the work per GPU, stays comparable (--scaling strong keeps --nsrc sources in total): every GPU holds the full grids
+list grows to N x 10^4 at a constant source density (weak scaling: the mesh grows with the volume, 256/320/400/512 for
+1/2/4/8 GPUs, same bubble radius, so the traces keep their length and every GPU has the same updates to do;
+--scaling strong keeps --mesh and --nsrc for the whole job): every GPU holds the full grids
 and traces its round-robin share (master_slave.F90:85), the partial rate grids are summed with ncclAllReduce
 (evolve.F90:599-602).  After the timed legs the sampled-source rate grid of the cpu_baseline leg is compared with
 the GPU's ("parity_rel_err", must be <= 1e-6).
@@ -78,8 +79,19 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
-def build_workload(mesh, nsrc_total, bubble):
-    """inputs of configs[2]/[3], deterministic; `bubble` = radius of the brightest source's sphere"""
+def job_shape(args, world):
+    """(mesh, sources in total, bubble radius) of the job on `world` GPUs.
+    weak scaling: --nsrc sources per GPU at a constant source density -- the mesh grows with the volume,
+    mesh = 16*round(--mesh * world^(1/3) / 16) (256, 320, 400, 512 for 1, 2, 4, 8 GPUs) -- and the same bubble radius,
+    so that the traces keep their length and every GPU has the same number of updates to do;
+    strong scaling: --mesh and --nsrc describe the whole job."""
+    if args.scaling == "strong" or world == 1:
+        return args.mesh, args.nsrc if args.scaling == "strong" else args.nsrc * world, args.bubble
+    mesh = int(round(args.mesh * world ** (1.0 / 3.0) / 16.0)) * 16
+    return mesh, args.nsrc * world, args.bubble
+
+
+def _build_workload(mesh, nsrc_total, bubble):
     from c2ray3dm_b200 import synthetic as syn
     zred = 9.0
     seed = 20240607 if mesh == 256 else (20240608 if mesh == 512 else 20240600 + mesh)
@@ -90,6 +102,35 @@ def build_workload(mesh, nsrc_total, bubble):
     dr, vol = syn.proper_geometry(mesh, zred)
     return dict(zred=zred, ndens=nd, srcpos=pos, normflux=nf, xh=xh, dr=dr, vol=vol,
                 clumping=syn.clumping_from_density(nd, zred), coldensh_LLS=syn.lls_coldens(dr[0], zred))
+
+
+def build_workload(mesh, nsrc_total, bubble):
+    """inputs of configs[2]/[3], deterministic; `bubble` = radius of the brightest source's sphere.
+    Under torchrun the local rank 0 builds them once and the other ranks of the node read them from /dev/shm."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 or not os.path.isdir("/dev/shm"):
+        return _build_workload(mesh, nsrc_total, bubble)
+    tag = "/dev/shm/c2b_workload_%s_%d_%d_%.4f_%s" % (os.environ.get("MASTER_PORT", "0"), mesh, nsrc_total, bubble,
+                                                      os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+    keys = ("ndens", "srcpos", "normflux", "xh", "dr", "clumping")
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        w = _build_workload(mesh, nsrc_total, bubble)
+        for k in keys:
+            np.save(tag + "_" + k + ".npy", w[k])
+        with open(tag + ".json.tmp", "w") as f:
+            json.dump({"zred": w["zred"], "vol": w["vol"], "coldensh_LLS": w["coldensh_LLS"]}, f)
+        os.rename(tag + ".json.tmp", tag + ".json")
+        return w
+    t0 = time.time()
+    while not os.path.exists(tag + ".json"):
+        time.sleep(0.5)
+        if time.time() - t0 > 1800:
+            raise SystemExit("bench.py: timed out waiting for local rank 0 to build the workload")
+    with open(tag + ".json") as f:
+        w = json.load(f)
+    for k in keys:
+        w[k] = np.load(tag + "_" + k + ".npy")
+    return w
 
 
 class ClockSampler(threading.Thread):
@@ -167,18 +208,17 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    strong = args.scaling == "strong"
-    w = build_workload(args.mesh, args.nsrc if strong else args.nsrc * args.gpus,
-                       args.bubble if strong else args.bubble * args.gpus ** (-1.0 / 3.0))
+    mesh_job, nsrc_total, bubble = job_shape(args, args.gpus)
+    w = build_workload(mesh_job, nsrc_total, bubble)
     nsample = args.cpu_sample or max(cores * 4, 64)
     rates, secs, upd = [], [], []
     desc = ""
     # size the sample towards ~10-20 s of CPU work per step (the whole run stays within minutes)
-    v, desc, s, u = cpu_sample(w, args.mesh, nsample, cores)
+    v, desc, s, u = cpu_sample(w, mesh_job, nsample, cores)
     if not args.cpu_sample:
         nsample = int(min(len(w["normflux"]), max(8, nsample * 12.0 / max(s, 1e-3))))
     for i in range(args.warmup + args.steps):
-        v, desc, s, u = cpu_sample(w, args.mesh, nsample, cores)
+        v, desc, s, u = cpu_sample(w, mesh_job, nsample, cores)
         if i >= args.warmup:
             rates.append(v)
             secs.append(s)
@@ -198,19 +238,18 @@ def run_reference(args):
 
 def workload_config(args, world=None):
     world = world or args.gpus
-    strong = args.scaling == "strong"
-    total = args.nsrc if strong else args.nsrc * world
-    bubble = args.bubble if strong else args.bubble * world ** (-1.0 / 3.0)
+    mesh, total, bubble = job_shape(args, world)
     return {"workload": "synthetic lognormal density %d^3, %d sources in total (%s) at density peaks, clumping grid "
                         "(type 5), LLS type 1, z=9, dt=%g Myr; every step = one evolve3D call from the same "
-                        "mid-reionization snapshot S1 (bubbles r<=%.1f cells, mean x=0.54 at 1 GPU), restored on the "
-                        "device before the call (BASELINE configs[%d])" % (
-                            args.mesh, total, "%d per GPU" % args.nsrc if not strong else "strong scaling", args.dt_myr,
-                            bubble, 3 if args.mesh == 512 else 2),
-            "mesh": args.mesh, "sources_total": total, "parallelism": "source-sharded x%d" % world,
+                        "mid-reionization snapshot S1 (bubbles r<=%.1f cells, mean x=0.54), restored on the "
+                        "device before the call (BASELINE configs[%d]%s)" % (
+                            mesh, total, "%d per GPU, constant source density: the mesh grows with the GPU count" % args.nsrc
+                            if args.scaling == "weak" else "strong scaling", args.dt_myr, bubble,
+                            3 if mesh == 512 else 2, "" if world == 1 or args.scaling == "strong" else ", weak-scaled"),
+            "mesh": mesh, "sources_total": total, "parallelism": "source-sharded x%d" % world,
             "state": "S1 restored every step (stationary)",
-            "l2": "grids (tau_cell + twin + phih + twin = %.0f MB) exceed the 126 MB L2" % (32 * args.mesh ** 3 / 1e6)
-            if args.mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
+            "l2": "grids (tau_cell + twin + phih + twin = %.0f MB) exceed the 126 MB L2" % (32 * mesh ** 3 / 1e6)
+            if mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
 
 
 def run_ours(args):
@@ -230,10 +269,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mesh = args.mesh
-    strong = args.scaling == "strong"
-    nsrc_total = args.nsrc if strong else args.nsrc * world
-    bubble = args.bubble if strong else args.bubble * world ** (-1.0 / 3.0)
+    mesh, nsrc_total, bubble = job_shape(args, world)
     w = build_workload(mesh, nsrc_total, bubble)
     dt = args.dt_myr * 1e6 * YEAR
 
@@ -299,6 +335,10 @@ def run_ours(args):
     barrier()
     wall = maxreduce(time.perf_counter() - t0)
     ms_rt_max = maxreduce(ms_rt)
+    # a rank that finishes its traces early waits inside the all-reduce: the smallest value over the ranks is the
+    # collective itself, the largest includes the wait for the slowest rank
+    ms_ar_min = -maxreduce(-ms_ar)
+    ms_ar_max = maxreduce(ms_ar)
     # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------
     # what fortran/evolve_b200.F90 moves per evolve3D call: ndens + xh in, xh + phih_grid out
     e2e = None
@@ -361,11 +401,13 @@ def run_ours(args):
                 "step_ms": step_ms,
                 "updates_per_step": upd / args.steps, "outer_iterations_per_step": niter / args.steps,
                 "gpu_launches": int(launches),
-                "phase_ms_per_step": {"raytrace": ms_rt / args.steps, "allreduce": ms_ar / args.steps,
+                "phase_ms_per_step": {"raytrace": ms_rt / args.steps, "raytrace_max_over_ranks": ms_rt_max / args.steps,
+                                      "allreduce": ms_ar / args.steps, "allreduce_min_over_ranks": ms_ar_min / args.steps,
+                                      "allreduce_max_over_ranks": ms_ar_max / args.steps,
                                       "chemistry": ms_chem / args.steps, "device_total": ms_dev / args.steps},
                 "roofline": {"kernel": "raytrace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": NCU_DRAM_BYTES_PER_UPDATE * upd_rank / max(1, niter) if args.mesh == 256 else None,
+                             "traffic": NCU_DRAM_BYTES_PER_UPDATE * upd_rank / max(1, niter) if mesh == 256 else None,
                              "traffic_note": "bytes per launch = %.1f B/update (ncu dram bytes of one launch of this "
                                              "workload, profiles/) x updates per launch" % NCU_DRAM_BYTES_PER_UPDATE,
                              "algorithmic_bytes_per_launch": B_RT * upd_rank / max(1, niter),

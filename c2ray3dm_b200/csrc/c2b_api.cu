@@ -60,6 +60,7 @@ struct c2b_handle {
   size_t ncell = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_step[2] = {nullptr, nullptr};   // brackets of c2b_evolve3d
   std::string error;
   // grids
   float* d_ndens = nullptr;
@@ -217,8 +218,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
       g_create_error = "c2b_create: mesh must be within [4, 4096] per axis";
       return 101;
     }
-  if ((double)cfg->mesh[0] * (double)cfg->mesh[1] * (double)cfg->mesh[2] >= 4294967296.0) {
-    g_create_error = "c2b_create: mesh(1)*mesh(2)*mesh(3) must be below 2^32 (cell indices are 32-bit on the device)";
+  if ((double)cfg->mesh[0] * (double)cfg->mesh[1] * (double)cfg->mesh[2] >= 2147483648.0) {
+    g_create_error = "c2b_create: mesh(1)*mesh(2)*mesh(3) must be below 2^31 (the reference's default-integer cell counts, evolve.F90:148,162)";
     return 101;
   }
   if (!cfg->isothermal) {
@@ -260,6 +261,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
     return bail("cudaStreamCreate", e);
   for (auto& ev : h->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  for (auto& ev : h->ev_step)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   const size_t n = h->ncell;
   if ((e = cudaMalloc(&h->d_ndens, n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc ndens", e);
@@ -340,6 +343,8 @@ void c2b_destroy(c2b_handle* h) {
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_small) cudaFreeHost(h->h_small);
   for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : h->ev_step)
     if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -786,10 +791,10 @@ int c2b_begin_step(c2b_handle* h, double* sum_xh) {
 
 int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_report* rep) {
   C2B_CHECK_H(h);
-  (void)niter;
   (void)dt;
   if (int rc = check_ready(h)) return rc;
   if (bind_device(h)) return 1;
+  h->iter_niter = niter;   // what write_iteration_dump would record after this pass (evolve.F90:309)
   // set_rates_to_zero, evolve.F90:430-440
   CU(h, cudaMemsetAsync(h->d_phih, 0, h->ncell * sizeof(double), h->stream));
   h->photon_loss = 0.0;
@@ -928,10 +933,7 @@ int c2b_evolve3d(c2b_handle* h, double time, double dt, int32_t restart, c2b_ste
   const c2b_config& c = h->cfg;
   const long long launches0 = h->launches;
   if (bind_device(h)) return 1;
-  cudaEvent_t t0, t1;
-  CU(h, cudaEventCreate(&t0));
-  CU(h, cudaEventCreate(&t1));
-  CU(h, cudaEventRecord(t0, h->stream));
+  CU(h, cudaEventRecord(h->ev_step[0], h->stream));
   int niter = 0;
   int conv_flag = c.mesh[0] * c.mesh[1] * c.mesh[2];
   // prev_sum_xh1_int=2.0*mesh(1)*mesh(2)*mesh(3): default-real arithmetic (evolve.F90:150-151)
@@ -954,6 +956,10 @@ int c2b_evolve3d(c2b_handle* h, double time, double dt, int32_t restart, c2b_ste
     if (!rc) {
       h->h0_before = h->h_stats[kH0] * h->vol;
       h->h1_before = h->h_stats[kH1] * h->vol;
+      // the restart branch does not touch prev_sum_xh*_int (evolve.F90:154-158): module variables without an
+      // initialiser, zero in a freshly started run, which is when a restart happens
+      prev_sum_xh1 = 0.0;
+      prev_sum_xh0 = 0.0;
       niter = h->iter_niter;
       c2b_global_report gr;
       rc = c2b_global_pass(h, dt, &gr);
@@ -1013,13 +1019,11 @@ int c2b_evolve3d(c2b_handle* h, double time, double dt, int32_t restart, c2b_ste
   rep->grtotal_ion = h->grtotal_ion;
   rep->grtotal_src = h->grtotal_src;
   h->have_iter_state = false;
-  CU(h, cudaEventRecord(t1, h->stream));
-  CU(h, cudaEventSynchronize(t1));
+  CU(h, cudaEventRecord(h->ev_step[1], h->stream));
+  CU(h, cudaEventSynchronize(h->ev_step[1]));
   float ms = 0.f;
-  CU(h, cudaEventElapsedTime(&ms, t0, t1));
+  CU(h, cudaEventElapsedTime(&ms, h->ev_step[0], h->ev_step[1]));
   rep->ms_total = ms;
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   rep->kernel_launches = h->launches - launches0;
   return 0;
 }

@@ -60,7 +60,13 @@ def sources_at_density_peaks(ndens, nsrc, max_normflux=1e7):
     """the `nsrc` densest cells (ties by linear index), descending density;
     NormFlux_s = max_normflux * n_s / max(n).  Returns (srcpos 1-based (nsrc,3), normflux)."""
     flat = ndens.reshape(-1)
-    order = np.lexsort((np.arange(flat.size), -flat.astype(np.float64)))[:nsrc]
+    if nsrc < flat.size:
+        # candidates: every cell at least as dense as the nsrc-th densest (a partition instead of a full sort)
+        kth = np.partition(flat, flat.size - nsrc)[flat.size - nsrc]
+        cand = np.flatnonzero(flat >= kth)
+    else:
+        cand = np.arange(flat.size)
+    order = cand[np.lexsort((cand, -flat[cand].astype(np.float64)))][:nsrc]
     n3, n2, n1 = ndens.shape
     k, rem = np.divmod(order, n2 * n1)
     j, i = np.divmod(rem, n1)

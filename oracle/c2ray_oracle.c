@@ -297,6 +297,10 @@ struct orc_state {
   int last_l[3], last_r[3], lastpos_l[3], lastpos_r[3];
   double photon_loss_src_thread;
   int64_t updates;
+  /* iteration dump (evolve.F90:285-324) kept in memory */
+  int dump_at_iter, have_dump, dump_niter;
+  double dump_photon_loss_all;
+  double *dump_phih, *dump_xh_av, *dump_xh_intermed;
 };
 
 orc_state *orc_create(int m1, int m2, int m3) {
@@ -326,6 +330,7 @@ void orc_destroy(orc_state *s) {
   free(s->ndens); free(s->xh); free(s->xh_av); free(s->xh_intermed); free(s->phih_grid);
   free(s->coldensh_out); free(s->clumping_grid); free(s->LLS_grid); free(s->srcpos);
   free(s->NormFlux_stellar);
+  free(s->dump_phih); free(s->dump_xh_av); free(s->dump_xh_intermed);
   free(s);
 }
 void orc_set_tables(orc_state *s, const double *thick, const double *thin) {
@@ -1021,17 +1026,62 @@ static double now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-/* evolve3D :83-281, restart == 0 */
-void orc_evolve3D(orc_state *s, double dt, int max_outer_iter, orc_step_report *rep) {
+/* write_iteration_dump :285-324 as an in-memory record: niter | photon_loss_all | phih_grid | xh_av | xh_intermed */
+static void write_iteration_dump(orc_state *s, int niter, double photon_loss_all) {
+  const size_t b = s->ncell * sizeof(double);
+  if (!s->dump_phih) {
+    s->dump_phih = (double *)malloc(b);
+    s->dump_xh_av = (double *)malloc(b);
+    s->dump_xh_intermed = (double *)malloc(b);
+  }
+  s->dump_niter = niter;
+  s->dump_photon_loss_all = photon_loss_all;
+  memcpy(s->dump_phih, s->phih_grid, b);
+  memcpy(s->dump_xh_av, s->xh_av, b);
+  memcpy(s->dump_xh_intermed, s->xh_intermed, b);
+  s->have_dump = 1;
+}
+
+/* The reference dumps when 15 minutes of wall clock have passed (:253-266); here the caller names the
+ * iteration after whose pass_all_sources the dump is taken (0 = never). */
+void orc_set_dump_iteration(orc_state *s, int niter) { s->dump_at_iter = niter; }
+
+int orc_get_dump(const orc_state *s, int *niter, double *photon_loss_all, double *phih, double *xh_av,
+                 double *xh_intermed) {
+  if (!s->have_dump) return 1;
+  const size_t b = s->ncell * sizeof(double);
+  *niter = s->dump_niter;
+  *photon_loss_all = s->dump_photon_loss_all;
+  memcpy(phih, s->dump_phih, b);
+  memcpy(xh_av, s->dump_xh_av, b);
+  memcpy(xh_intermed, s->dump_xh_intermed, b);
+  return 0;
+}
+
+/* evolve3D :83-281.  restart != 0: start_from_dump (:328-426) has put niter, photon_loss_all, phih_grid, xh_av
+ * and xh_intermed in place (orc_evolve3D_restart), then global_pass runs before the loop (:154-158). */
+static void evolve3D_impl(orc_state *s, double dt, int max_outer_iter, int restart, int niter0,
+                          double photon_loss_all0, orc_step_report *rep) {
   memset(rep, 0, sizeof(*rep));
   orc_state_before(s); /* :136 */
-  memcpy(s->xh_av, s->xh, s->ncell * sizeof(double));       /* :140-147 */
-  memcpy(s->xh_intermed, s->xh, s->ncell * sizeof(double));
   int niter = 0;
   int conv_flag = s->mesh[0] * s->mesh[1] * s->mesh[2];
   double prev_sum_xh1_int = (double)(2.0f * (float)s->mesh[0] * (float)s->mesh[1] * (float)s->mesh[2]);
   double prev_sum_xh0_int = prev_sum_xh1_int;
   double rel_change_sum_xh1 = 1.0, rel_change_sum_xh0 = 1.0;
+  if (restart == 0) {
+    memcpy(s->xh_av, s->xh, s->ncell * sizeof(double));       /* :140-147 */
+    memcpy(s->xh_intermed, s->xh, s->ncell * sizeof(double));
+  } else {
+    /* the restart branch leaves prev_sum_xh*_int as they are: module variables without initialiser (:69-70),
+     * zero in a freshly started run, which is when a restart happens */
+    prev_sum_xh1_int = 0.0;
+    prev_sum_xh0_int = 0.0;
+    niter = niter0;
+    orc_global_report gr0;
+    orc_global_pass(s, dt, photon_loss_all0, &gr0); /* :157 */
+    conv_flag = gr0.conv_flag;
+  }
   /* :162-163 */
   int c1 = (int)(K_convergence_fraction * (double)s->mesh[0] * (double)s->mesh[1] * (double)s->mesh[2]);
   int c2 = (s->NumSrc - 1) / 3;
@@ -1068,6 +1118,7 @@ void orc_evolve3D(orc_state *s, double dt, int max_outer_iter, orc_step_report *
     double t0 = now_s();
     orc_pass_all_sources(s, &pr);
     double t1 = now_s();
+    if (s->dump_at_iter == niter) write_iteration_dump(s, niter, pr.photon_loss_all); /* :253-266 */
     orc_global_report gr;
     orc_global_pass(s, dt, pr.photon_loss_all, &gr);
     double t2 = now_s();
@@ -1092,4 +1143,19 @@ void orc_evolve3D(orc_state *s, double dt, int max_outer_iter, orc_step_report *
   s->grtotal_ion = s->grtotal_ion + s->total_ion - s->totcollisions;
   rep->grtotal_ion = s->grtotal_ion;
   rep->grtotal_src = s->grtotal_src;
+}
+
+void orc_evolve3D(orc_state *s, double dt, int max_outer_iter, orc_step_report *rep) {
+  evolve3D_impl(s, dt, max_outer_iter, 0, 0, 0.0, rep);
+}
+
+/* evolve3D(time,dt,restart/=0): the dump record is passed in instead of read from iterdump[12].bin */
+void orc_evolve3D_restart(orc_state *s, double dt, int max_outer_iter, int niter, double photon_loss_all,
+                          const double *phih, const double *xh_av, const double *xh_intermed,
+                          orc_step_report *rep) {
+  const size_t b = s->ncell * sizeof(double);
+  memcpy(s->phih_grid, phih, b);
+  memcpy(s->xh_av, xh_av, b);
+  memcpy(s->xh_intermed, xh_intermed, b);
+  evolve3D_impl(s, dt, max_outer_iter, 1, niter, photon_loss_all, rep);
 }

@@ -147,6 +147,18 @@ typedef struct orc_step_report {
 /* evolve.F90:83-281 with restart==0.  max_outer_iter<=0 means the reference's limit (niter>100). */
 void orc_evolve3D(orc_state *s, double dt, int max_outer_iter, orc_step_report *rep);
 
+/* write_iteration_dump / start_from_dump, evolve.F90:285-426.  The reference dumps between pass_all_sources and
+ * global_pass once 15 minutes have passed (:253-266); here the caller names the iteration (0 = never) and reads
+ * the record (niter | photon_loss_all | phih_grid | xh_av | xh_intermed, :309-317) back with orc_get_dump.
+ * orc_evolve3D_restart is evolve3D(time,dt,restart/=0): the record replaces iterdump[12].bin, xh must hold the
+ * state of the start of the step, and global_pass runs once before the loop continues at niter+1 (:154-158). */
+void orc_set_dump_iteration(orc_state *s, int niter);
+int orc_get_dump(const orc_state *s, int *niter, double *photon_loss_all, double *phih, double *xh_av,
+                 double *xh_intermed);
+void orc_evolve3D_restart(orc_state *s, double dt, int max_outer_iter, int niter, double photon_loss_all,
+                          const double *phih, const double *xh_av, const double *xh_intermed,
+                          orc_step_report *rep);
+
 #ifdef __cplusplus
 }
 #endif

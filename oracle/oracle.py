@@ -120,6 +120,10 @@ def lib():
         L.orc_state_before.argtypes = [vp]
         L.orc_calculate_photon_statistics.argtypes = [vp, C.c_double, dp, dp, C.POINTER(PhotonStats)]
         L.orc_evolve3D.argtypes = [vp, C.c_double, C.c_int, C.POINTER(StepReport)]
+        L.orc_set_dump_iteration.argtypes = [vp, C.c_int]
+        L.orc_get_dump.argtypes = [vp, C.POINTER(C.c_int), dp, dp, dp, dp]
+        L.orc_evolve3D_restart.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_double, dp, dp, dp,
+                                           C.POINTER(StepReport)]
         _lib = L
     return _lib
 
@@ -305,4 +309,25 @@ class Oracle:
     def evolve3D(self, dt, max_outer_iter=0):
         r = StepReport()
         self.L.orc_evolve3D(self.h, float(dt), int(max_outer_iter), C.byref(r))
+        return r
+
+    def set_dump_iteration(self, niter):
+        """write_iteration_dump (evolve.F90:285-324) after pass_all_sources of iteration `niter` (0 = never)"""
+        self.L.orc_set_dump_iteration(self.h, int(niter))
+
+    def get_dump(self):
+        """(niter, photon_loss_all, phih_grid, xh_av, xh_intermed) of the last dump, or None"""
+        n = C.c_int()
+        pl = C.c_double()
+        g = [np.empty(self.shape, dtype=np.float64) for _ in range(3)]
+        if self.L.orc_get_dump(self.h, C.byref(n), C.byref(pl), _dp(g[0]), _dp(g[1]), _dp(g[2])):
+            return None
+        return n.value, pl.value, g[0], g[1], g[2]
+
+    def evolve3D_restart(self, dt, niter, photon_loss_all, phih, xh_av, xh_intermed, max_outer_iter=0):
+        """evolve3D(time,dt,restart/=0) with the dump record in place of iterdump[12].bin (evolve.F90:154-158)"""
+        r = StepReport()
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (phih, xh_av, xh_intermed)]
+        self.L.orc_evolve3D_restart(self.h, float(dt), int(max_outer_iter), int(niter), float(photon_loss_all),
+                                    _dp(a[0]), _dp(a[1]), _dp(a[2]), C.byref(r))
         return r

@@ -81,8 +81,8 @@ def test_bad_config_is_rejected_before_touching_cuda():
     cfg.mesh[0] = 2
     assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 101 and not h.value
     cfg = L.default_config()
-    cfg.mesh[0], cfg.mesh[1], cfg.mesh[2] = 2048, 2048, 2048      # 2^33 cells: 32-bit cell indices would overflow
-    assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 101 and b"2^32" in lib.c2b_last_error(None)
+    cfg.mesh[0], cfg.mesh[1], cfg.mesh[2] = 2048, 2048, 2048      # 2^33 cells: default-integer cell counts would overflow
+    assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 101 and b"2^31" in lib.c2b_last_error(None)
     cfg = L.default_config()
     cfg.isothermal = 0
     assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 102

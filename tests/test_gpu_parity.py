@@ -238,34 +238,56 @@ def test_against_committed_golden(name):
     e.close()
 
 
-def test_restart_from_iteration_state(gpu_tables):
-    """get/set_iter_state (iterdump, evolve.F90:285-426): stopping after 2 outer iterations and restarting
-    reaches the same converged answer as an uninterrupted call"""
+def test_restart_from_iteration_dump(gpu_tables):
+    """write_iteration_dump / start_from_dump (evolve.F90:285-426).  The reference dumps between pass_all_sources
+    and global_pass; the shim does the same with the fine-grained calls.  The dump record taken after the pass of
+    iteration 2 matches the oracle's, and a fresh handle restarted from it (restart /= 0: global_pass, then the
+    loop continues at niter+1) finishes exactly like the uninterrupted run, and like the oracle's restart."""
     p = _problem(CASES[5])
+    # uninterrupted runs
     e = setup_gpu(p, tables=gpu_tables)
     full = e.evolve3D(0.0, DT)
-    x_full = e.xh
-    e2 = setup_gpu(p, tables=gpu_tables, max_outer_iter=1)
-    part = e2.evolve3D(0.0, DT)
-    assert part.converged == 0 and part.niter == 2
-    niter, pl, phih, xav, xint = e2.get_iter_state()
+    x_full, xav_full, ph_full = e.xh, e.xh_av, e.phih_grid
+    o = setup_oracle(p, tables=gpu_tables)
+    o.set_dump_iteration(2)
+    ro = o.evolve3D(DT)
+    assert full.niter == ro.niter > 2
+    dump_o = o.get_dump()
+    # the host's loop up to the dump point of iteration 2 (fortran/evolve_b200.F90)
+    e2 = setup_gpu(p, tables=gpu_tables)
+    e2.begin_step()
+    for niter in (1, 2):
+        e2.pass_all_sources(niter, DT)
+        if niter == 2:
+            dump_g = e2.get_iter_state()
+        e2.global_pass(DT)
+    assert dump_g[0] == dump_o[0] == 2
+    assert dump_g[1] == pytest.approx(dump_o[1], rel=RATE_RTOL)
+    _rates_close(dump_g[2], dump_o[2])
+    np.testing.assert_allclose(dump_g[3], dump_o[3], rtol=0, atol=X_ATOL)
+    np.testing.assert_allclose(dump_g[4], dump_o[4], rtol=0, atol=X_ATOL)
+    # restart a fresh handle (xh = start of the step, as the xfrac file holds it) from the GPU's dump
     e3 = setup_gpu(p, tables=gpu_tables)
-    e3.set_iter_state(niter, pl, phih, xav, xint)
+    e3.set_iter_state(*dump_g)
     rest = e3.evolve3D(0.0, DT, restart=1)
-    # the restart repeats one global_pass on the dumped state (evolve.F90:157), so it may need one more
-    # outer iteration and lands on the same fixed point within the outer convergence criterion
-    assert rest.converged == 1 and part.niter <= rest.niter <= full.niter + 1
-    # same fixed point within the outer convergence criterion (relative change of sum(x) < 1e-4 per
-    # iteration, evolve.F90:212-214), not bit-identical: the restart adds one global_pass
-    x_rest = e3.xh
-    assert abs(x_rest.sum() - x_full.sum()) / x_full.sum() < 1e-3
-    assert np.max(np.abs(x_rest - x_full)) < 2e-2
-    # the dump itself round-trips exactly
-    n2, pl2, ph2, xa2, xi2 = e2.get_iter_state()
-    e3.set_iter_state(n2, pl2, ph2, xa2, xi2)
-    n3, pl3, ph3, xa3, xi3 = e3.get_iter_state()
-    assert (n3, pl3) == (n2, pl2)
-    for u, v in ((ph2, ph3), (xa2, xa3), (xi2, xi3)):
+    assert (rest.niter, rest.converged) == (full.niter, full.converged)
+    assert list(rest.conv_flag[3:rest.niter + 1]) == list(full.conv_flag[3:full.niter + 1])
+    np.testing.assert_allclose(e3.xh, x_full, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(e3.xh_av, xav_full, rtol=0, atol=1e-12)
+    # the last rate grid was accumulated with atomics in both runs: equal up to the order of the additions
+    np.testing.assert_allclose(e3.phih_grid, ph_full, rtol=1e-10, atol=0)
+    assert rest.final_stats.photcons == pytest.approx(full.final_stats.photcons, rel=1e-10)
+    # the oracle restarted from ITS dump agrees too
+    o2 = setup_oracle(p, tables=gpu_tables)
+    r2 = o2.evolve3D_restart(DT, *dump_o)
+    assert (rest.niter, rest.converged) == (r2.niter, r2.converged)
+    assert list(rest.conv_flag[3:rest.niter + 1]) == list(r2.conv_flag[3:r2.niter + 1])
+    np.testing.assert_allclose(e3.xh, o2.xh, rtol=0, atol=X_ATOL)
+    assert rest.final_stats.photcons == pytest.approx(r2.final_stats.photcons, rel=1e-6)
+    # the dump itself round-trips exactly through the ABI
+    n3, pl3, ph3, xa3, xi3 = (e3.set_iter_state(*dump_g), e3.get_iter_state())[1]
+    assert (n3, pl3) == (dump_g[0], dump_g[1])
+    for u, v in ((dump_g[2], ph3), (dump_g[3], xa3), (dump_g[4], xi3)):
         np.testing.assert_array_equal(u, v)
     for x in (e, e2, e3):
         x.close()
