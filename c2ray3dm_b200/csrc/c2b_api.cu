@@ -69,6 +69,13 @@ struct c2b_handle {
   double *d_thick = nullptr, *d_thin = nullptr, *d_taucell = nullptr;
   double *d_taucell_t = nullptr, *d_phih_t = nullptr;   // y-fastest twins for the x-principal quadrants
   double* d_xh_saved = nullptr;                         // c2b_save_xh_dev
+  // non-isothermal path
+  double *d_phiheat = nullptr, *d_phiheat_t = nullptr;  // evolve_data.F90:42 and its y-fastest twin
+  double *d_heat_thick = nullptr, *d_heat_thin = nullptr, *d_cie_cool = nullptr;
+  double2* d_heat2 = nullptr;
+  float *d_Tcur = nullptr, *d_Tavg = nullptr, *d_Tint = nullptr, *d_Taos = nullptr;   // temperature_grid
+  double cool_mintemp = 0.0, cool_dtemp = 1.0, zred = 0.0;
+  bool have_heat_tables = false, have_cooling = false;
   bool taucell_t_dirty = true;
   double2 *d_thick2 = nullptr, *d_logtab = nullptr;
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
@@ -196,6 +203,15 @@ int c2b_default_config(c2b_config* c) {
   c->temph0 = eth0 * ev2k;                                 // :80
   c->colh0 = (double)1.3e-8f * (double)0.83f * (double)1.0f / (eth0 * eth0);  // :86
   c->abu_c = (double)7.1e-7f;                              // abundances.f90:26
+  c->k_B = 1.381e-16;                                      // cgsconstants.f90:34
+  c->gamma1 = 5.0 / 3.0 - 1.0;                             // atomic.f90:23-25
+  c->minitemp = (double)1.0f;                              // c2ray_parameters.f90:108
+  c->relative_denergy = (double)0.1f;                      // :110
+  c->tau_heat_limit = (double)1.0e-4f;                     // radiation_photoionrates.F90:333
+  const double Mpc = (double)1e6f * (double)3.086e18f;     // cgsastroconstants.f90:29-31
+  c->H0 = (double)0.7f * (double)100.0f * (double)1e5f / Mpc;   // cosmoparms.f90:28,41
+  c->Omega0 = (double)0.27f;                               // :30
+  c->cosmological = 1;                                     // c2ray_parameters.f90:105
   return 0;
 }
 
@@ -221,10 +237,6 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((double)cfg->mesh[0] * (double)cfg->mesh[1] * (double)cfg->mesh[2] >= 2147483648.0) {
     g_create_error = "c2b_create: mesh(1)*mesh(2)*mesh(3) must be below 2^31 (the reference's default-integer cell counts, evolve.F90:148,162)";
     return 101;
-  }
-  if (!cfg->isothermal) {
-    g_create_error = "c2b_create: only isothermal=.true. is implemented (thermal.f90 needs tables/corocool.tab, absent from the reference)";
-    return 102;
   }
   if (cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks) {
     g_create_error = "c2b_create: bad rank/nranks";
@@ -278,6 +290,23 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMalloc(&h->d_taucell_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell_t", e);
   if ((e = cudaMalloc(&h->d_phih_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phih_t", e);
   if ((e = cudaMalloc(&h->d_thick2, kTableLen * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
+  if (!cfg->isothermal) {
+    if ((e = cudaMalloc(&h->d_phiheat, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phiheat", e);
+    if ((e = cudaMalloc(&h->d_phiheat_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phiheat_t", e);
+    if ((e = cudaMemsetAsync(h->d_phiheat, 0, n * sizeof(double), h->stream)) != cudaSuccess) return bail("memset", e);
+    if ((e = cudaMalloc(&h->d_heat_thick, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_heat_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_heat2, kTableLen * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_cie_cool, 64 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_Tcur, n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc T", e);
+    if ((e = cudaMalloc(&h->d_Tavg, n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc T", e);
+    if ((e = cudaMalloc(&h->d_Tint, n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc T", e);
+    if ((e = cudaMalloc(&h->d_Taos, 3 * n * sizeof(float))) != cudaSuccess) return bail("cudaMalloc T", e);
+    // temperature_array_init (temperature_module.F90:44-67) with the default temper_val
+    launch_fill_f32(h->d_Tcur, (float)h->temper_val, n, h->stream);
+    launch_fill_f32(h->d_Tavg, (float)h->temper_val, n, h->stream);
+    launch_fill_f32(h->d_Tint, (float)h->temper_val, n, h->stream);
+  }
   if ((e = cudaMalloc(&h->d_logtab, 128 * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc", e);
   {
     // log2 table of the table-coordinate evaluation (raytrace.cu: table_coord)
@@ -298,7 +327,7 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
     smax = std::max(smax, std::max(h->lim[d][0], h->lim[d][1]));
   }
   h->plane_stride = smax + 1;
-  if (raytrace_configure(smax, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
+  if (raytrace_configure(smax, !cfg->isothermal, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
   h->rt_grid = h->rt.grid_max;
   h->cluster_max_sources = 4 * h->rt.clusters;
   if (const char* env = getenv("C2B_CLUSTER_MIN_NBOX")) h->cluster_min_nbox = atoi(env);
@@ -337,6 +366,8 @@ void c2b_destroy(c2b_handle* h) {
   cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_taucell_t); cudaFree(h->d_phih_t); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
   cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_xh_saved);
+  cudaFree(h->d_phiheat); cudaFree(h->d_phiheat_t); cudaFree(h->d_heat_thick); cudaFree(h->d_heat_thin); cudaFree(h->d_heat2);
+  cudaFree(h->d_cie_cool); cudaFree(h->d_Tcur); cudaFree(h->d_Tavg); cudaFree(h->d_Tint); cudaFree(h->d_Taos);
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -406,11 +437,16 @@ int c2b_rad_ini_blackbody(c2b_handle* h, double T_eff, double S_star, double fre
   sp.hplanck = hplanck; sp.k_B = k_B; sp.two_pi_over_c_square = two_pi_over_c_square;
   sp.R_solar = R_solar; sp.pi = h->cfg.pi; sp.pl_index_cross_section = pl_index_cross_section;
   sp.minlogtau = h->cfg.minlogtau; sp.dlogtau = h->cfg.dlogtau;
-  int rc = build_blackbody_tables(sp, h->d_thick, h->d_thin, h->stream, nullptr);
+  int rc = build_blackbody_tables(sp, h->d_thick, h->d_thin, h->d_heat_thick, h->d_heat_thin, h->stream, nullptr);
   h->launches += 1;
   if (rc) return fail(h, "c2b_rad_ini_blackbody: table kernel failed");
   launch_pair_table(h->d_thick, h->d_thick2, h->stream);
   h->launches += 1;
+  if (h->d_heat_thick) {
+    launch_pair_table(h->d_heat_thick, h->d_heat2, h->stream);
+    h->launches += 1;
+    h->have_heat_tables = true;
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   h->have_tables = true;
   if (thick_out) CU(h, cudaMemcpy(thick_out, h->d_thick, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
@@ -496,6 +532,14 @@ int c2b_set_temperature(c2b_handle* h, double t) {
   C2B_CHECK_H(h);
   if (!(t > 0)) return fail(h, "c2b_set_temperature: temperature must be positive");
   h->temper_val = t;
+  if (h->d_Tcur) {   // temperature_array_init, temperature_module.F90:44-67
+    if (bind_device(h)) return 1;
+    launch_fill_f32(h->d_Tcur, (float)t, h->ncell, h->stream);
+    launch_fill_f32(h->d_Tavg, (float)t, h->ncell, h->stream);
+    launch_fill_f32(h->d_Tint, (float)t, h->ncell, h->stream);
+    h->launches += 3;
+    CU(h, cudaGetLastError());
+  }
   return 0;
 }
 
@@ -579,6 +623,89 @@ int c2b_set_xh(c2b_handle* h, const double* xh) {
   return 0;
 }
 
+// ---- non-isothermal inputs ------------------------------------------------------------------------
+static int need_thermal(c2b_handle* h, const char* who) {
+  if (h->cfg.isothermal) {
+    h->error = std::string(who) + ": the handle was created with isothermal=.true.";
+    return 3;
+  }
+  return 0;
+}
+
+int c2b_set_heat_tables(c2b_handle* h, const double* thick, const double* thin, int32_t n) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_set_heat_tables")) return rc;
+  if (!thick || !thin) return fail(h, "c2b_set_heat_tables: null table");
+  if (n != kTableLen) return fail(h, "c2b_set_heat_tables: n must be NumTau+1 = 2001");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_heat_thick, thick, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_heat_thin, thin, kTableLen * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  launch_pair_table(h->d_heat_thick, h->d_heat2, h->stream);
+  h->launches += 1;
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->have_heat_tables = true;
+  return 0;
+}
+
+int c2b_get_heat_tables(c2b_handle* h, double* thick, double* thin) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_get_heat_tables")) return rc;
+  if (!h->have_heat_tables) return fail(h, "c2b_get_heat_tables: heat tables not set");
+  if (!thick || !thin) return fail(h, "c2b_get_heat_tables: null pointer");
+  if (bind_device(h)) return 1;
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(thick, h->d_heat_thick, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
+  CU(h, cudaMemcpy(thin, h->d_heat_thin, kTableLen * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int c2b_set_cooling_table(c2b_handle* h, const double* log10_temp, const double* log10_cool, int32_t n) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_set_cooling_table")) return rc;
+  if (!log10_temp || !log10_cool) return fail(h, "c2b_set_cooling_table: null pointer");
+  if (n != 61) return fail(h, "c2b_set_cooling_table: the CIE table has 61 rows (cooling.f90:29)");
+  if (bind_device(h)) return 1;
+  double cie[64] = {0};
+  for (int i = 0; i < 61; ++i) cie[i] = std::pow(10.0, log10_cool[i]);   // cooling.f90:84-86
+  h->cool_mintemp = log10_temp[0];                                       // :79-80
+  h->cool_dtemp = log10_temp[1] - log10_temp[0];
+  if (!(h->cool_dtemp > 0)) return fail(h, "c2b_set_cooling_table: temperatures must increase");
+  CU(h, cudaMemcpy(h->d_cie_cool, cie, sizeof(cie), cudaMemcpyHostToDevice));
+  h->have_cooling = true;
+  return 0;
+}
+
+int c2b_set_redshift(c2b_handle* h, double zred) {
+  C2B_CHECK_H(h);
+  if (!(zred > -1.0)) return fail(h, "c2b_set_redshift: zred must exceed -1");
+  h->zred = zred;
+  return 0;
+}
+
+int c2b_set_temperature_grid(c2b_handle* h, const float* tg) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_set_temperature_grid")) return rc;
+  if (!tg) return fail(h, "c2b_set_temperature_grid: null pointer");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_Taos, tg, 3 * h->ncell * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  launch_unpack_temperature(h->d_Taos, h->d_Tcur, h->d_Tavg, h->d_Tint, h->ncell, h->stream);
+  h->launches += 1;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int c2b_get_temperature_grid(c2b_handle* h, float* tg) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_get_temperature_grid")) return rc;
+  if (!tg) return fail(h, "c2b_get_temperature_grid: null pointer");
+  if (bind_device(h)) return 1;
+  launch_pack_temperature(h->d_Tcur, h->d_Tavg, h->d_Tint, h->d_Taos, h->ncell, h->stream);
+  h->launches += 1;
+  CU(h, cudaMemcpyAsync(tg, h->d_Taos, 3 * h->ncell * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 // ---- internals of the hot path ------------------------------------------------------------------
 static void fill_chem(c2b_handle* h, double dt, ChemParams& cp) {
   const c2b_config& c = h->cfg;
@@ -606,6 +733,23 @@ static void fill_chem(c2b_handle* h, double dt, ChemParams& cp) {
   cp.partials = h->d_partials;
   cp.tau_cell = h->d_taucell;
   cp.sigma_dr0 = c.sigma_HI * h->dr[0];
+  cp.temph0 = c.temph0;
+  cp.albpow = c.albpow;
+  cp.temper_val = T;
+  cp.T_cur = nullptr; cp.T_avg = nullptr; cp.T_int = nullptr; cp.phiheat = nullptr; cp.cie_cool = nullptr;
+  cp.cool_mintemp = cp.cool_dtemp = cp.k_B = cp.gamma1 = cp.minitemp = cp.relative_denergy = cp.cosmo_cool_factor = 0.0;
+  if (!c.isothermal) {
+    cp.T_cur = h->d_Tcur; cp.T_avg = h->d_Tavg; cp.T_int = h->d_Tint;
+    cp.phiheat = h->d_phiheat;
+    cp.cie_cool = h->d_cie_cool;
+    cp.cool_mintemp = h->cool_mintemp; cp.cool_dtemp = h->cool_dtemp;
+    cp.k_B = c.k_B; cp.gamma1 = c.gamma1; cp.minitemp = c.minitemp; cp.relative_denergy = c.relative_denergy;
+    if (c.cosmological) {   // cosmo_cool = e_int*2.0/(1.0+zred)*dzdt, cosmology.F90:198-225
+      const double z1 = 1.0 + h->zred;
+      const double dzdt = c.H0 * z1 * std::sqrt(c.Omega0 * (z1 * z1 * z1) + 1.0 - c.Omega0);
+      cp.cosmo_cool_factor = 2.0 / z1 * dzdt;
+    }
+  }
 }
 
 static int fetch_stats(c2b_handle* h) {
@@ -625,6 +769,10 @@ static int check_ready(c2b_handle* h) {
   if (h->cfg.type_of_clumping >= 3 && !h->d_clump) return fail(h, "clumping grid not set");
   if (h->cfg.use_LLS && h->cfg.type_of_LLS == 2 && !h->d_lls) return fail(h, "LLS grid not set");
   if (h->cfg.nranks > 1 && !h->comm) return fail(h, "nranks > 1 but c2b_comm_init was not called");
+  if (!h->cfg.isothermal) {
+    if (!h->have_heat_tables) return fail(h, "heating tables not set (c2b_set_heat_tables / c2b_rad_ini_blackbody)");
+    if (!h->have_cooling) return fail(h, "cooling table not set (c2b_set_cooling_table)");
+  }
   return 0;
 }
 
@@ -678,6 +826,11 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.thick2 = h->d_thick2;
   rp.thin = h->d_thin;
   rp.logtab = h->d_logtab;
+  rp.heat2 = h->d_heat2;
+  rp.heat_thin = h->d_heat_thin;
+  rp.phiheat = h->d_phiheat;
+  rp.phiheat_t = h->d_phiheat_t;
+  rp.tau_heat_limit = c.tau_heat_limit;
   rp.srcpos = h->d_srcpos;
   rp.normflux = h->d_normflux;
   rp.work = d_work;
@@ -723,6 +876,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     h->taucell_t_dirty = false;
   }
   CU(h, cudaMemsetAsync(h->d_phih_t, 0, h->ncell * sizeof(double), h->stream));
+  if (h->d_phiheat_t) CU(h, cudaMemsetAsync(h->d_phiheat_t, 0, h->ncell * sizeof(double), h->stream));
   CU(h, cudaMemsetAsync(h->d_ticket, 0, 2 * sizeof(unsigned int), h->stream));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   if (nwork_cl > 0) {  // long traces first: one cluster per source, planes in shared memory
@@ -747,6 +901,10 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   if (nwork > 0 || nwork_cl > 0) {
     launch_add_from_yfast(h->d_phih, h->d_phih_t, c.mesh, h->stream);
     h->launches += 1;
+    if (h->d_phiheat) {
+      launch_add_from_yfast(h->d_phiheat, h->d_phiheat_t, c.mesh, h->stream);
+      h->launches += 1;
+    }
     CU(h, cudaGetLastError());
   }
   CU(h, cudaEventRecord(h->ev[1], h->stream));
@@ -797,6 +955,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
   h->iter_niter = niter;   // what write_iteration_dump would record after this pass (evolve.F90:309)
   // set_rates_to_zero, evolve.F90:430-440
   CU(h, cudaMemsetAsync(h->d_phih, 0, h->ncell * sizeof(double), h->stream));
+  if (h->d_phiheat) CU(h, cudaMemsetAsync(h->d_phiheat, 0, h->ncell * sizeof(double), h->stream));   // :435
   h->photon_loss = 0.0;
   h->LLS_loss = 0.0;
   float ms_rt = 0.f, ms_ar = 0.f;
@@ -855,6 +1014,8 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     h->h_small[0] = loss_sum; h->h_small[1] = nbox_sum; h->h_small[2] = upd_sum; h->h_small[3] = 0.0;
     CU(h, cudaMemcpyAsync(h->d_small, h->h_small, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     NC(h, g_nccl.AllReduce(h->d_phih, h->d_phih, h->ncell, ncclDouble, ncclSum, h->comm, h->stream));
+    if (h->d_phiheat)   // evolve.F90:604-609
+      NC(h, g_nccl.AllReduce(h->d_phiheat, h->d_phiheat, h->ncell, ncclDouble, ncclSum, h->comm, h->stream));
     NC(h, g_nccl.AllReduce(h->d_small, h->d_small, 4, ncclDouble, ncclSum, h->comm, h->stream));
     CU(h, cudaMemcpyAsync(h->h_small, h->d_small, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaEventRecord(h->ev[3], h->stream));
@@ -908,8 +1069,11 @@ int c2b_end_step(c2b_handle* h, double dt, int32_t converged, c2b_photon_stats* 
   C2B_CHECK_H(h);
   if (int rc = check_ready(h)) return rc;
   if (bind_device(h)) return 1;
-  if (converged)  // xh(:,:,:)=xh_intermed(:,:,:), evolve.F90:215-217
+  if (converged) {  // xh(:,:,:)=xh_intermed(:,:,:), evolve.F90:215-217
     CU(h, cudaMemcpyAsync(h->d_xh, h->d_xh_intermed, h->ncell * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->d_Tcur)  // set_final_temperature_point (:218, temperature_module.F90:173-183): current=intermed
+      CU(h, cudaMemcpyAsync(h->d_Tcur, h->d_Tint, h->ncell * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
   // calculate_photon_statistics(dt,xh,xh_av), evolve.F90:277
   ChemParams cp;
   fill_chem(h, dt, cp);
@@ -1043,6 +1207,28 @@ int c2b_get_xh(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p,
 int c2b_get_xh_av(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_xh_av, h->ncell * 8, "c2b_get_xh_av"); }
 int c2b_get_xh_intermed(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_xh_intermed, h->ncell * 8, "c2b_get_xh_intermed"); }
 int c2b_get_phih(c2b_handle* h, double* p) { C2B_CHECK_H(h); return download(h, p, h->d_phih, h->ncell * 8, "c2b_get_phih"); }
+int c2b_get_phiheat(c2b_handle* h, double* p) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_get_phiheat")) return rc;
+  return download(h, p, h->d_phiheat, h->ncell * 8, "c2b_get_phiheat");
+}
+int c2b_get_iter_state_thermal(c2b_handle* h, double* phiheat, float* tg) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_get_iter_state_thermal")) return rc;
+  int rc = 0;
+  if (phiheat && (rc = c2b_get_phiheat(h, phiheat))) return rc;
+  if (tg && (rc = c2b_get_temperature_grid(h, tg))) return rc;
+  return 0;
+}
+int c2b_set_iter_state_thermal(c2b_handle* h, const double* phiheat, const float* tg) {
+  C2B_CHECK_H(h);
+  if (int rc = need_thermal(h, "c2b_set_iter_state_thermal")) return rc;
+  if (!phiheat || !tg) return fail(h, "c2b_set_iter_state_thermal: null pointer");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(h->d_phiheat, phiheat, h->ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return c2b_set_temperature_grid(h, tg);
+}
 int c2b_get_phih_f32(c2b_handle* h, float* p) {
   C2B_CHECK_H(h);
   if (!p) return fail(h, "c2b_get_phih_f32: null pointer");

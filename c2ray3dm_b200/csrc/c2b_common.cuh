@@ -35,6 +35,12 @@ struct RtParams {
   const double2* thick2;    // stellar_photo_thick_table as (value, forward difference) pairs
   const double* thin;       // stellar_photo_thin_table(0:NumTau,1)
   const double2* logtab;    // 128 x {1/c_j, A + B*log2(c_j)}
+  // non-isothermal path (null when isothermal): stellar_heat_thick_table as pairs, ..thin.., phiheat_grid + twin
+  const double2* heat2;
+  const double* heat_thin;
+  double* phiheat;
+  double* phiheat_t;
+  double tau_heat_limit;    // radiation_photoionrates.F90:333
   const int* srcpos;        // 3 x NumSrc, 1-based (sourceprops.F90:56)
   const double* normflux;   // NormFlux_stellar(1:NumSrc)
   const int* work;          // source indices (0-based) this rank traces, in order
@@ -70,7 +76,7 @@ struct RtLaunchInfo {
   int grid_max;    // CTAs the scratch must be sized for
 };
 // sets the kernels' shared-memory attributes and queries the resident grid sizes
-int raytrace_configure(int max_radius, RtLaunchInfo* info);
+int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info);
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream);
 void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl);
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
@@ -106,12 +112,27 @@ struct ChemParams {
   double* partials;        // [nblocks][kNumStat]
   double* tau_cell;        // out (chemistry kernel): opacity grid for the next ray trace, or nullptr
   double sigma_dr0;
+  // non-isothermal path (all null / unused when isothermal): temperature_grid as three float arrays
+  const float* T_cur;      // temperature_grid%current (start of the step)
+  float* T_avg;            // %average: in = previous iterate, out = new time average
+  float* T_int;            // %intermed: out
+  const double* phiheat;   // evolve_data.F90:42
+  const double* cie_cool;  // 61 entries, cooling.f90:29
+  double cool_mintemp, cool_dtemp;
+  double k_B, gamma1, minitemp, relative_denergy;
+  double cosmo_cool_factor;   // 2/(1+zred)*dzdt (cosmology.F90:198-225), 0 when not cosmological
+  double temph0, albpow;
+  double temper_val;       // isothermal temperature (unused otherwise)
 };
 
 void launch_chemistry(const ChemParams& p, int nblocks, cudaStream_t stream);
 // statistics only: sum(x_l), h0/h1 from (ndens,x_l); totrec/totcoll from (ndens,x_r) (x_r may be null)
 void launch_stats(const ChemParams& p, const double* x_l, const double* x_r, int nblocks,
                   cudaStream_t stream);
+// temperature_grid (current, average, intermed per cell, default real) <-> three float arrays
+void launch_unpack_temperature(const float* aos, float* cur, float* avg, float* inter, size_t n, cudaStream_t stream);
+void launch_pack_temperature(const float* cur, const float* avg, const float* inter, float* aos, size_t n, cudaStream_t stream);
+void launch_fill_f32(float* a, float v, size_t n, cudaStream_t stream);
 void launch_finalize_partials(const double* partials, int nblocks, double* out /*kNumStat*/,
                               cudaStream_t stream);
 void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream);
@@ -126,8 +147,8 @@ struct SedParams {
   double pl_index_cross_section;
   double minlogtau, dlogtau;
 };
-int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin, cudaStream_t stream,
-                           double* S_star_unscaled_out);
+int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin, double* d_heat_thick,
+                           double* d_heat_thin, cudaStream_t stream, double* S_star_unscaled_out);
 
 double measure_dfma_rate(cudaStream_t stream);
 

@@ -74,54 +74,179 @@ __device__ __forceinline__ void doric(double dt, double rhe, double brech0, doub
   if (xav0 < eps) xav0 = eps;
 }
 
-__global__ void __launch_bounds__(kThreads) chemistry_kernel(ChemParams P) {
-  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, -1.0e300, 0.0};
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  for (size_t c = (size_t)blockIdx.x * kThreads + threadIdx.x; c < P.ncell; c += stride) {
-    // evolve0D_global, evolve_point.F90:348-353 (no epsilon clamp on the neutral fractions)
-    const double xav_prev = P.xh_av[c];
-    const double h_old1 = fmax(P.epsilon, P.xh[c]);
-    const double h_old0 = 1.0 - h_old1;
-    double h_av1 = fmax(P.epsilon, xav_prev);
-    double h_av0 = 1.0 - h_av1;
-    const double ndens_p = (double)P.ndens[c];
-    const double phih = P.phih[c];
-    const float clump = P.clumping_grid ? P.clumping_grid[c] : P.clumping;  // clumping_point
-    const double brech0 = (double)clump * P.bh00 * P.powT;                  // doric.f90:74
-    double h1 = 0.0, h0 = 0.0;
-    // do_chemistry, evolve_point.F90:448-551
-    int nit = 0;
-    for (;;) {
-      nit += 1;
-      const double yh0_av_old = h_av0;
-      const double de = ndens_p * (h_av1 + P.abu_c);  // electrondens, tped.f90:75-83
-      doric(P.dt, de, brech0, P.acolh0, phih, P.epsilon, h_old1, h_old0, h1, h0, h_av1, h_av0);
-      if (fabs((h_av0 - yh0_av_old) / h_av0) < P.minimum_fractional_change ||
-          h_av0 < P.minimum_fraction_of_atoms)
-        break;
-      if (nit > 400) break;  // 'Convergence failing (global)'
+// doric.f90:33-134 with its own temperature-dependent coefficients (non-isothermal path: temp0 changes per cell
+// and per iteration of do_chemistry)
+__device__ __forceinline__ void doric_T(const ChemParams& P, double temp0, float clump, double rhe, double phih,
+                                        double xold1, double xold0, double& x1, double& x0, double& xav1,
+                                        double& xav0) {
+  const double brech0 = (double)clump * P.bh00 * pow(temp0 / (double)1e4f, P.albpow);   // doric.f90:74
+  const double acolh0 = P.colh0 * sqrt(temp0) * exp(-P.temph0 / temp0);                 // :76-77
+  doric(P.dt, rhe, brech0, acolh0, phih, P.epsilon, xold1, xold0, x1, x0, xav1, xav0);
+}
+
+// coolin, cooling.f90:38-59 (the 61-entry CIE curve sits in shared memory)
+__device__ __forceinline__ double coolin(const ChemParams& P, const double* s_cool, double nucldens, double eldens,
+                                         double temp0) {
+  const double tpos = (log10(temp0) - P.cool_mintemp) / P.cool_dtemp + 1.0;
+  int itpos = (int)tpos;
+  itpos = min(61 - 1, max(1, itpos));
+  const double dtpos = tpos - (double)itpos;
+  const int itpos1 = min(61, itpos + 1);
+  return nucldens * eldens * (s_cool[itpos - 1] + (s_cool[itpos1 - 1] - s_cool[itpos - 1]) * dtpos);
+}
+
+// thermal, thermal.f90:22-176: explicit sub-cycled energy equation of one cell
+__device__ __forceinline__ void thermal(const ChemParams& P, const double* s_cool, double initial_temperature,
+                                        double& final_temperature, double& average_temperature,
+                                        double ndens_electron, double ndens_atom, double h1, double hold1,
+                                        double hav1, double heating) {
+  const double dt = P.dt;
+  // temper2pressr(T, n, electrondens(n, h_old))/gamma1, tped.f90:41-53,75-83
+  double internal_energy = (ndens_atom + ndens_atom * (hold1 + P.abu_c)) * P.k_B * initial_temperature / P.gamma1;
+  const double cosmo_cool_rate = internal_energy * P.cosmo_cool_factor;   // e_int*2.0/(1.0+zred)*dzdt
+  if (!(initial_temperature > P.minitemp)) return;
+  const double npe_av = ndens_atom + ndens_atom * (hav1 + P.abu_c);
+  double cumulative_time = 0.0, avg = 0.0;
+  double intermediate_temperature = initial_temperature;
+  int i_heating = 0;
+  for (;;) {
+    i_heating += 1;
+    const double cooling = coolin(P, s_cool, ndens_atom, ndens_electron, intermediate_temperature) + cosmo_cool_rate;
+    const double thermal_rate = fmax(1e-50, fabs(cooling - heating));
+    const double thermal_timescale = internal_energy / fabs(thermal_rate);
+    const double dt_thermal = P.relative_denergy * thermal_timescale;
+    const double dt_ODE = fmin(dt_thermal, dt - cumulative_time);
+    internal_energy = internal_energy + dt_ODE * (heating - cooling);
+    avg = avg + 0.5 * intermediate_temperature * dt_ODE;
+    intermediate_temperature = internal_energy * P.gamma1 / (P.k_B * npe_av);   // pressr2temper
+    avg = avg + 0.5 * intermediate_temperature * dt_ODE;
+    if (intermediate_temperature < P.minitemp) {   // thermal.f90:129-136 (no division by gamma1 there)
+      internal_energy = npe_av * P.k_B * P.minitemp;
+      intermediate_temperature = P.minitemp;
     }
-    // convergence against the previous iterate, evolve_point.F90:378-391
-    const double yh0_prev = 1.0 - fmax(P.epsilon, xav_prev);
-    const double dabs = fabs(h_av0 - yh0_prev);
-    if (dabs > P.minimum_fractional_change &&
-        fabs((h_av0 - yh0_prev) / h_av0) > P.minimum_fractional_change &&
-        h_av0 > P.minimum_fraction_of_atoms)
-      acc.conv += 1.0;
-    P.xh_intermed[c] = h1;  // :400-401
-    P.xh_av[c] = h_av1;
-    // opacity grid for the next ray trace: the h_av(0) evolve0D will form from this xh_av
-    // (evolve_point.F90:137-142) times ndens times sigma_HI*dr(1)
-    if (P.tau_cell) P.tau_cell[c] = P.sigma_dr0 * (fmax(1.0 - fmax(h_av1, P.epsilon), P.epsilon) * ndens_p);
-    // fused reductions
-    acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
-    acc.sum_x += h1;                                       // :565
-    acc.h0 += ndens_p * (1.0 - h1);                        // state_after(xh_intermed)
-    acc.h1 += ndens_p * h1;
-    const double yh1 = h_av1, yh0 = 1.0 - h_av1;           // total_rates(dt,xh_av)
-    const double ne = ndens_p * (yh1 + P.abu_c);
+    cumulative_time = cumulative_time + dt_ODE;
+    if (cumulative_time >= dt || fabs(cumulative_time - dt) < (double)1e-6f * dt) break;
+    if (i_heating > 10000) break;
+  }
+  average_temperature = (dt > 0.0) ? avg / dt : initial_temperature;
+  final_temperature = internal_energy * P.gamma1 / (P.k_B * (ndens_atom + ndens_atom * (h1 + P.abu_c)));
+}
+
+// one cell of global_pass: evolve0D_global + do_chemistry (evolve_point.F90:305-555) and the fused reductions
+template <bool kThermal>
+__device__ __forceinline__ void chem_cell(const ChemParams& P, const double* s_cool, size_t c, double xh_c,
+                                          double xav_prev, double phih, float ndens_f, float clump,
+                                          double& out_intermed, double& out_av, double& out_tau, Acc& acc) {
+  // evolve0D_global, evolve_point.F90:348-353 (no epsilon clamp on the neutral fractions)
+  const double h_old1 = fmax(P.epsilon, xh_c);
+  const double h_old0 = 1.0 - h_old1;
+  double h_av1 = fmax(P.epsilon, xav_prev);
+  double h_av0 = 1.0 - h_av1;
+  const double ndens_p = (double)ndens_f;
+  const double brech0 = (double)clump * P.bh00 * P.powT;                  // doric.f90:74
+  double h1 = 0.0, h0 = 0.0;
+  // temperature_start / temperature_end of do_chemistry (:441-444)
+  double T_start_cur = 0.0, T_start_avg = 0.0, T_end_avg = 0.0, T_end_int = 0.0, heat = 0.0;
+  if (kThermal) {
+    T_start_cur = (double)P.T_cur[c];
+    T_start_avg = (double)P.T_avg[c];
+    T_end_avg = T_start_avg;
+    T_end_int = (double)P.T_int[c];
+    heat = P.phiheat[c];
+  }
+  // do_chemistry, evolve_point.F90:448-551
+  int nit = 0;
+  for (;;) {
+    nit += 1;
+    const double yh0_av_old = h_av0;
+    double de = ndens_p * (h_av1 + P.abu_c);  // electrondens, tped.f90:75-83
+    if (kThermal) {
+      doric_T(P, T_end_avg, clump, de, phih, h_old1, h_old0, h1, h0, h_av1, h_av0);
+      de = ndens_p * (h_av1 + P.abu_c);
+      thermal(P, s_cool, T_start_cur, T_end_int, T_end_avg, de, ndens_p, h1, h_old1, h_av1, heat);   // :519-526
+    } else {
+      doric(P.dt, de, brech0, P.acolh0, phih, P.epsilon, h_old1, h_old0, h1, h0, h_av1, h_av0);
+    }
+    // (the temperature term of :530-535 compares temperature_end%current, which never changes)
+    if (fabs((h_av0 - yh0_av_old) / h_av0) < P.minimum_fractional_change || h_av0 < P.minimum_fraction_of_atoms)
+      break;
+    if (nit > 400) break;  // 'Convergence failing (global)'
+  }
+  double T_new_avg = 0.0;
+  if (kThermal) {   // set_temperature_point (:553): intermed and average, stored as default real
+    const float fa = (float)T_end_avg;
+    P.T_int[c] = (float)T_end_int;
+    P.T_avg[c] = fa;
+    T_new_avg = (double)fa;
+  }
+  // convergence against the previous iterate, evolve_point.F90:378-391
+  const double yh0_prev = 1.0 - fmax(P.epsilon, xav_prev);
+  const double dabs = fabs(h_av0 - yh0_prev);
+  bool unconverged = dabs > P.minimum_fractional_change &&
+                     fabs((h_av0 - yh0_prev) / h_av0) > P.minimum_fractional_change &&
+                     h_av0 > P.minimum_fraction_of_atoms;
+  if (kThermal)
+    unconverged = unconverged || (fabs((T_start_avg - T_new_avg) / T_new_avg) > 1.0e-1 &&
+                                  fabs(T_start_avg - T_new_avg) > 100.0);
+  if (unconverged) acc.conv += 1.0;
+  out_intermed = h1;  // :400-401
+  out_av = h_av1;
+  // opacity grid for the next ray trace: the h_av(0) evolve0D will form from this xh_av
+  // (evolve_point.F90:137-142) times ndens times sigma_HI*dr(1)
+  out_tau = P.sigma_dr0 * (fmax(1.0 - fmax(h_av1, P.epsilon), P.epsilon) * ndens_p);
+  // fused reductions
+  acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
+  acc.sum_x += h1;                                       // :565
+  acc.h0 += ndens_p * (1.0 - h1);                        // state_after(xh_intermed)
+  acc.h1 += ndens_p * h1;
+  const double yh1 = h_av1, yh0 = 1.0 - h_av1;           // total_rates(dt,xh_av)
+  const double ne = ndens_p * (yh1 + P.abu_c);
+  if (kThermal) {   // temperature%average of the cell, photonstatistics.F90:166-176
+    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * pow(T_new_avg / (double)1e4f, P.albpow);
+    acc.coll += ndens_p * yh0 * ne * P.colh0 * sqrt(T_new_avg) * exp(-P.temph0 / T_new_avg);
+  } else {
     acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
     acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+  }
+}
+
+// Two cells per thread: every grid is read and written with 128-bit (double2) / 64-bit (float2) accesses.
+template <bool kThermal>
+__global__ void __launch_bounds__(kThreads) chemistry_kernel(ChemParams P) {
+  __shared__ double s_cool[64];
+  if (kThermal) {
+    if (threadIdx.x < 61) s_cool[threadIdx.x] = P.cie_cool[threadIdx.x];
+    __syncthreads();
+  }
+  Acc acc = {0.0, 0.0, 0.0, 0.0, 0.0, -1.0e300, 0.0};
+  const size_t npair = P.ncell >> 1;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const double2* xh2 = reinterpret_cast<const double2*>(P.xh);
+  double2* xav2 = reinterpret_cast<double2*>(P.xh_av);
+  double2* xint2 = reinterpret_cast<double2*>(P.xh_intermed);
+  const double2* ph2 = reinterpret_cast<const double2*>(P.phih);
+  const float2* nd2 = reinterpret_cast<const float2*>(P.ndens);
+  const float2* cl2 = reinterpret_cast<const float2*>(P.clumping_grid);
+  double2* tau2 = reinterpret_cast<double2*>(P.tau_cell);
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < npair; i += stride) {
+    const double2 x = xh2[i], xa = xav2[i], ph = ph2[i];
+    const float2 nd = nd2[i];
+    const float2 cl = P.clumping_grid ? cl2[i] : make_float2(P.clumping, P.clumping);  // clumping_point
+    double2 oi, oa, ot;
+    chem_cell<kThermal>(P, s_cool, 2 * i, x.x, xa.x, ph.x, nd.x, cl.x, oi.x, oa.x, ot.x, acc);
+    chem_cell<kThermal>(P, s_cool, 2 * i + 1, x.y, xa.y, ph.y, nd.y, cl.y, oi.y, oa.y, ot.y, acc);
+    xint2[i] = oi;
+    xav2[i] = oa;
+    if (P.tau_cell) tau2[i] = ot;
+  }
+  if ((P.ncell & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd cell count: the last cell
+    const size_t c = P.ncell - 1;
+    double oi, oa, ot;
+    chem_cell<kThermal>(P, s_cool, c, P.xh[c], P.xh_av[c], P.phih[c], P.ndens[c],
+                        P.clumping_grid ? P.clumping_grid[c] : P.clumping, oi, oa, ot, acc);
+    P.xh_intermed[c] = oi;
+    P.xh_av[c] = oa;
+    if (P.tau_cell) P.tau_cell[c] = ot;
   }
   block_store(acc, P.partials);
 }
@@ -141,8 +266,14 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(ChemParams P, const dou
       const double yh1 = x_r[c], yh0 = 1.0 - yh1;
       const float clump = P.clumping_grid ? P.clumping_grid[c] : P.clumping;
       const double ne = ndens_p * (yh1 + P.abu_c);
-      acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
-      acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+      if (P.T_avg) {   // temperature%average of the cell (non-isothermal), photonstatistics.F90:166-176
+        const double Ta = (double)P.T_avg[c];
+        acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * pow(Ta / (double)1e4f, P.albpow);
+        acc.coll += ndens_p * yh0 * ne * P.colh0 * sqrt(Ta) * exp(-P.temph0 / Ta);
+      } else {
+        acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
+        acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+      }
       acc.maxav = fmax(acc.maxav, yh1);
     }
   }
@@ -167,6 +298,27 @@ __global__ void scale_density_kernel(float* ndens, size_t n, double zfactor3) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride)
     ndens[c] = (float)((double)ndens[c] / zfactor3);
+}
+
+__global__ void unpack_temperature_kernel(const float* __restrict__ aos, float* cur, float* avg, float* inter, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    cur[c] = aos[3 * c];
+    avg[c] = aos[3 * c + 1];
+    inter[c] = aos[3 * c + 2];
+  }
+}
+__global__ void pack_temperature_kernel(const float* cur, const float* avg, const float* inter, float* __restrict__ aos, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    aos[3 * c] = cur[c];
+    aos[3 * c + 1] = avg[c];
+    aos[3 * c + 2] = inter[c];
+  }
+}
+__global__ void fill_f32_kernel(float* a, float v, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) a[c] = v;
 }
 
 __global__ void to_f32_kernel(const double* in, float* out, size_t n) {
@@ -229,7 +381,8 @@ int chemistry_blocks() {
 }
 
 void launch_chemistry(const ChemParams& p, int nblocks, cudaStream_t stream) {
-  chemistry_kernel<<<nblocks, kThreads, 0, stream>>>(p);
+  if (p.T_cur) chemistry_kernel<true><<<nblocks, kThreads, 0, stream>>>(p);
+  else chemistry_kernel<false><<<nblocks, kThreads, 0, stream>>>(p);
 }
 void launch_stats(const ChemParams& p, const double* x_l, const double* x_r, int nblocks,
                   cudaStream_t stream) {
@@ -240,6 +393,15 @@ void launch_finalize_partials(const double* partials, int nblocks, double* out, 
 }
 void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream) {
   scale_density_kernel<<<chemistry_blocks(), 256, 0, stream>>>(ndens, n, zfactor3);
+}
+void launch_unpack_temperature(const float* aos, float* cur, float* avg, float* inter, size_t n, cudaStream_t stream) {
+  unpack_temperature_kernel<<<chemistry_blocks(), 256, 0, stream>>>(aos, cur, avg, inter, n);
+}
+void launch_pack_temperature(const float* cur, const float* avg, const float* inter, float* aos, size_t n, cudaStream_t stream) {
+  pack_temperature_kernel<<<chemistry_blocks(), 256, 0, stream>>>(cur, avg, inter, aos, n);
+}
+void launch_fill_f32(float* a, float v, size_t n, cudaStream_t stream) {
+  fill_f32_kernel<<<chemistry_blocks(), 256, 0, stream>>>(a, v, n);
 }
 void launch_to_f32(const double* in, float* out, size_t n, cudaStream_t stream) {
   to_f32_kernel<<<chemistry_blocks(), 256, 0, stream>>>(in, out, n);

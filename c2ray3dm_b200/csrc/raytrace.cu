@@ -98,6 +98,7 @@ struct Face {
   double dP2, dA2, dB2;       // dr^2 per axis (dist2 of evolve_point.F90:170-174)
   const double* tau;          // opacity grid (x-fastest, or the y-fastest twin for p == 2)
   double* phih;               // rate grid, same layout
+  double* heat;               // heating-rate grid (phiheat_grid or its twin), non-isothermal only
 };
 
 // max/min of two NON-NEGATIVE doubles through their bit patterns (integer order == numeric order there);
@@ -173,10 +174,13 @@ __device__ __forceinline__ double lerp_pairs(const double2* __restrict__ tab, do
 
 // photoion_rates / photo_lookuptable (radiation_photoionrates.F90:71-317) for one stellar source:
 // Gamma_cell*vol_ph = F*(thick(tau_in)-thick(tau_out)), or F*dtau*thin(tau_in) below tau_photo_limit.
+// kHeat adds heat_lookuptable (:323-417) on the same table positions: heat*vol_ph = F*(H(tau_in)-H(tau_out)), or
+// F*dtau*Hthin(tau_in) below tau_heat_limit.
+template <bool kHeat>
 __device__ __forceinline__ void photo_rates(double tau_in, double tau_out, double normflux,
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
-                                            const double* __restrict__ thin, double tau_photo_limit, const LogC& L,
-                                            double& phi_all, double& phi_out) {
+                                            const double2* __restrict__ s_heat, const RtParams& P, const LogC& L,
+                                            double& phi_all, double& phi_out, double& heat_all) {
   // both table coordinates are formed together (two independent chains); the thin branch overrides
   const double od_in = table_coord(tau_in, s_logtab, L);
   const double od_out = table_coord(tau_out, s_logtab, L);
@@ -186,11 +190,19 @@ __device__ __forceinline__ void photo_rates(double tau_in, double tau_out, doubl
   phi_out = normflux * lerp_pairs(s_thick, od_out, ipos2, res2);
   phi_all = phi_in - phi_out;
   const double dtau = tau_out - tau_in;
-  if (!(fabs(dtau) > tau_photo_limit)) {
-    const double lo = thin[ipos];
-    const double th = lo + (thin[min(kNumTau, ipos + 1)] - lo) * res;
+  if (!(fabs(dtau) > P.tau_photo_limit)) {
+    const double lo = P.thin[ipos];
+    const double th = lo + (P.thin[min(kNumTau, ipos + 1)] - lo) * res;
     phi_all = normflux * dtau * th;
     phi_out = phi_in - phi_all;
+  }
+  if (kHeat) {
+    const double2 hi_ = s_heat[ipos], ho_ = s_heat[ipos2];
+    heat_all = normflux * fma(hi_.y, res, hi_.x) - normflux * fma(ho_.y, res2, ho_.x);
+    if (!(fabs(dtau) > P.tau_heat_limit)) {
+      const double lo = P.heat_thin[ipos];
+      heat_all = normflux * dtau * (lo + (P.heat_thin[min(kNumTau, ipos + 1)] - lo) * res);
+    }
   }
 }
 
@@ -247,10 +259,10 @@ struct SrcCtx {
 // The kFpg faces `faces[0..kFpg)` are walked by kTg threads (this thread is number `gtid`); prev/cur are the plane
 // buffers of the first face, those of the next faces follow at `fstride` doubles.  min_hi returns the high word of
 // the smallest optical depth written (the dead-face rule in the kernel).
-template <int kFpg, int kTg, bool kGlobal, bool kClip, bool kR1, int kLls, bool kDebug>
+template <int kFpg, int kTg, bool kGlobal, bool kClip, bool kR1, int kLls, bool kDebug, bool kHeat>
 __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, const Face* __restrict__ faces, int gtid,
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
-                                            const LogC& L, int r, const double* __restrict__ prev,
+                                            const double2* __restrict__ s_heat, const LogC& L, int r, const double* __restrict__ prev,
                                             double* __restrict__ cur, int fstride, int nseg, double& loss, int& min_hi) {
   if (kGlobal) {
     __builtin_assume(__isGlobal(prev));
@@ -305,8 +317,10 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
     int posBp = wrap(F.srcB + b0, nB), posBm = wrap(F.srcB - b0, nB);
     const double* __restrict__ g_tau = F.tau;
     double* __restrict__ g_phih = F.phih;
+    double* __restrict__ g_heat = F.heat;
     __builtin_assume(__isGlobal(g_tau));
     __builtin_assume(__isGlobal(g_phih));
+    if (kHeat) __builtin_assume(__isGlobal(g_heat));
     // column geometry shared by the four quadrants
     const double ad = (double)a;
     const double ua = (a == r) ? 1.0 : ad * inv_r;    // 1-dx of cinterp
@@ -418,12 +432,16 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
             if (kDebug) P.coldens_dbg[xfast_index(P, F.p, cell)] = out.v[j] * P.inv_sigma;
             if (!(tin[jj] > P.tau_stop) && !stop_all) {    // evolve_point.F90:201
               const double tau_cell = tc.v[j];
-              double phi_all, phi_out;
-              photo_rates(tin[jj], out.v[j], S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
+              double phi_all, phi_out, heat_all = 0.0;
+              photo_rates<kHeat>(tin[jj], out.v[j], S.normflux, s_thick, s_logtab, s_heat, P, L, phi_all, phi_out, heat_all);
               // vol_ph = 4*pi*dist2*path (evolve_point.F90:170-177); rate = phi_all/(vol_ph*nHI)
               const double inv_vol = fast_rcp(volk * tau_cell);
               const double photo_cell = phi_all * inv_vol;            // :262
               if (photo_cell != 0.0) atomicAdd(&g_phih[cell], photo_cell);   // :283-284
+              if (kHeat) {   // phi%heat = heat_all/vol_ph, not divided by the neutral density (:285-286)
+                const double heat_cell = heat_all * (inv_vol * (tau_cell * P.inv_sigma_dr0));
+                if (heat_cell != 0.0) atomicAdd(&g_heat[cell], heat_cell);
+              }
               // boundary of this pass's subbox (:290-295): photo_out*vol/vol_ph
               if ((lossmask >> j) & 1u) loss = fma(phi_out * P.vol, inv_vol * (tau_cell * P.inv_sigma_dr0), loss);
             }
@@ -440,13 +458,14 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
 }
 
 // One CTA (kCluster == 1, all six faces) or one cluster of 6 CTAs (one face each) per source.
-template <int kCluster, int kLls, bool kDebug>
+template <int kCluster, int kLls, bool kDebug, bool kHeat>
 __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
   constexpr int kNf = kFaces / kCluster;            // faces handled by this CTA
   extern __shared__ double2 smem2[];
   double2* s_thick = smem2;                         // kTableLen pairs
   double2* s_logtab = smem2 + kTableLen;            // 128 pairs
-  double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128);
+  double2* s_heat = smem2 + kTableLen + 128;        // kTableLen pairs (non-isothermal only)
+  double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128 + (kHeat ? kTableLen : 0));
   __shared__ Face s_face[kNf];
   __shared__ double s_red[kT / 32];
   __shared__ double s_slot[2][8];                   // per-face boundary loss, alternating by pass (rank 0's copy is used)
@@ -466,6 +485,8 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
   const int cap = (kCluster == 1) ? P.smem_plane_doubles : P.smem_plane_doubles_cl;   // one shared plane buffer of one face
   for (int i = tid; i < kTableLen; i += kT) s_thick[i] = P.thick2[i];
   for (int i = tid; i < 128; i += kT) s_logtab[i] = P.logtab[i];
+  if (kHeat)
+    for (int i = tid; i < kTableLen; i += kT) s_heat[i] = P.heat2[i];
   for (int i = tid; i < 2 * kNf * (cap + kPadFront); i += kT) s_planes[i] = 0.0;
   // every face owns two fixed plane buffers (faces run decoupled, so their storage must not move with r):
   // `cap` doubles each in shared memory, Gf each in the global scratch slot of the work group
@@ -542,6 +563,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
         F.dB2 = (p == 0) ? P.dr2[1] : P.dr2[2];
         F.tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
         F.phih = (p == 2) ? P.phih_t : P.phih;
+        F.heat = (p == 2) ? P.phiheat_t : P.phiheat;
         s_face[tid] = F;
       }
       double loss = 0.0;
@@ -556,11 +578,15 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
           if (crank == 0 && tid == 0) {
             if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
             if (S.normflux > 0.0) {
-              double phi_all, phi_out;
-              photo_rates(0.0, tau_out, S.normflux, s_thick, s_logtab, P.thin, P.tau_photo_limit, L, phi_all, phi_out);
+              double phi_all, phi_out, heat_all = 0.0;
+              photo_rates<kHeat>(0.0, tau_out, S.normflux, s_thick, s_logtab, s_heat, P, L, phi_all, phi_out, heat_all);
               // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
               const double photo_cell = phi_all * fast_rcp(P.vol_cell * tau_cell * P.inv_sigma_dr0);
               if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);
+              if (kHeat) {
+                const double heat_cell = heat_all * fast_rcp(P.vol_cell);
+                if (heat_cell != 0.0) atomicAdd(&P.phiheat[cell], heat_cell);
+              }
             }
           }
         }
@@ -581,9 +607,9 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
           if (cur_sm) {
             double* cur = (r & 1) ? sbuf1 : sbuf0;
             const double* prev = (r & 1) ? sbuf0 : sbuf1;
-            if (r == 1) trace_shell<kFpg, kTg, false, false, true, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
-            else if (r < S.rsafe) trace_shell<kFpg, kTg, false, false, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
-            else trace_shell<kFpg, kTg, false, true, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            if (r == 1) trace_shell<kFpg, kTg, false, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, false, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            else trace_shell<kFpg, kTg, false, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
           } else {
             double* cur = (r & 1) ? gbuf1 : gbuf0;
             double* gprev = (r & 1) ? gbuf0 : gbuf1;
@@ -594,9 +620,9 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
                 for (int i = gtid; i < 4 * r * r; i += kTg) gprev[f * gstride + i] = sprev[f * sstride + i];
               group_sync<kTg>(g);
             }
-            if (r == 1) trace_shell<kFpg, kTg, true, false, true, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
-            else if (r < S.rsafe) trace_shell<kFpg, kTg, true, false, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
-            else trace_shell<kFpg, kTg, true, true, false, kLls, kDebug>(P, S, faces, gtid, s_thick, s_logtab, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            if (r == 1) trace_shell<kFpg, kTg, true, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, true, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            else trace_shell<kFpg, kTg, true, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
           }
         }
         // plane r complete before plane r+1 reads it.  Dead-face rule: once every optical depth of the planes of a
@@ -676,25 +702,35 @@ size_t raytrace_scratch_doubles_per_cta(int plane_stride) {
 }
 
 // plane_doubles = capacity of one plane buffer of one face; a CTA holds two per face
-static size_t rt_smem_bytes(int plane_doubles, int nfaces) {
-  return (size_t)(kTableLen + 128) * sizeof(double2) + (size_t)2 * nfaces * (plane_doubles + kPadFront) * sizeof(double);
+static size_t rt_smem_bytes(int plane_doubles, int nfaces, bool heat) {
+  return (size_t)(kTableLen + 128 + (heat ? kTableLen : 0)) * sizeof(double2) +
+         (size_t)2 * nfaces * (plane_doubles + kPadFront) * sizeof(double);
 }
 
 typedef void (*RtKernel)(RtParams);
 
+// lls: 0/1 = scalar (0: no LLS, a zero column), 2 = LLS_grid, 3 = R_max; the diagnostic (debug) kernels exist for
+// the isothermal path only
 template <int kCluster>
-static RtKernel pick_kernel(int lls, bool debug) {
+static RtKernel pick_kernel(int lls, bool debug, bool heat) {
   if (debug) {
     switch (lls) {
-      case 2: return raytrace_kernel<kCluster, 2, true>;
-      case 3: return raytrace_kernel<kCluster, 3, true>;
-      default: return raytrace_kernel<kCluster, 1, true>;
+      case 2: return raytrace_kernel<kCluster, 2, true, false>;
+      case 3: return raytrace_kernel<kCluster, 3, true, false>;
+      default: return raytrace_kernel<kCluster, 1, true, false>;
+    }
+  }
+  if (heat) {
+    switch (lls) {
+      case 2: return raytrace_kernel<kCluster, 2, false, true>;
+      case 3: return raytrace_kernel<kCluster, 3, false, true>;
+      default: return raytrace_kernel<kCluster, 1, false, true>;
     }
   }
   switch (lls) {
-    case 2: return raytrace_kernel<kCluster, 2, false>;
-    case 3: return raytrace_kernel<kCluster, 3, false>;
-    default: return raytrace_kernel<kCluster, 1, false>;
+    case 2: return raytrace_kernel<kCluster, 2, false, false>;
+    case 3: return raytrace_kernel<kCluster, 3, false, false>;
+    default: return raytrace_kernel<kCluster, 1, false, false>;
   }
 }
 
@@ -713,39 +749,40 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, i
   cfg->numAttrs = 1;
 }
 
-int raytrace_configure(int max_radius, RtLaunchInfo* info) {
+int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info) {
   int dev = 0, max_optin = 0, sm_total = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const size_t fixed = (size_t)(kTableLen + 128) * sizeof(double2);
+  const size_t fixed = (size_t)(kTableLen + 128 + (heat_tables ? kTableLen : 0)) * sizeof(double2);
   // kCtaPerSm CTAs per SM share the opt-in shared memory; what the tables leave goes to the plane buffers
-  int per_cta = std::min(std::min(max_optin, sm_total / kCtaPerSm - 2048), 56 * 1024);   // the rest of the SM's 256 KB is L1 for the global planes
+  int per_cta = std::min(std::min(max_optin, sm_total / kCtaPerSm - 2048), (heat_tables ? 88 : 56) * 1024);   // the rest of the SM's 256 KB is L1 for the global planes
   if (const char* env = getenv("C2B_RT_SMEM_KB")) per_cta = std::min(std::min(max_optin, sm_total / kCtaPerSm - 2048), atoi(env) * 1024);
   const int avail = (int)(((size_t)per_cta - fixed - 1024) / sizeof(double));   // doubles for all plane buffers of a CTA
   const int full = 4 * (max_radius + 1) * (max_radius + 1) + 4 * (max_radius + 1) + 8;   // one face at the largest radius
   const int cap_cta = std::max(64, std::min(avail / (2 * kFaces) - kPadFront, full)) & ~3;
   const int cap_cl = std::max(64, std::min(avail / 2 - kPadFront, full)) & ~3;
-  for (int dbg = 0; dbg < 2; ++dbg)
+  for (int var = 0; var < 3; ++var)   // 0: plain, 1: diagnostic, 2: with heating rates
     for (int lls = 1; lls < 4; ++lls) {
-      cudaError_t e = cudaFuncSetAttribute(pick_kernel<1>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)rt_smem_bytes(cap_cta, kFaces));
+      const bool dbg = var == 1, heat = var == 2;
+      cudaError_t e = cudaFuncSetAttribute(pick_kernel<1>(lls, dbg, heat), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)rt_smem_bytes(cap_cta, kFaces, heat));
       if (e != cudaSuccess) return (int)e;
-      e = cudaFuncSetAttribute(pick_kernel<kClusterSize>(lls, dbg != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)rt_smem_bytes(cap_cl, 1));
+      e = cudaFuncSetAttribute(pick_kernel<kClusterSize>(lls, dbg, heat), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)rt_smem_bytes(cap_cl, 1, heat));
       if (e != cudaSuccess) return (int)e;
     }
   info->smem_plane_doubles = cap_cta;
   info->smem_plane_doubles_cl = cap_cl;
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<1>(1, false), kT, rt_smem_bytes(cap_cta, kFaces));
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_kernel<1>(1, false, heat_tables), kT, rt_smem_bytes(cap_cta, kFaces, heat_tables));
   info->grid_cta = sms * std::max(1, per_sm);
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, sms, rt_smem_bytes(cap_cl, 1), nullptr);
+  cluster_config(&cfg, attr, sms, rt_smem_bytes(cap_cl, 1, heat_tables), nullptr);
   int nclusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, pick_kernel<kClusterSize>(1, false), &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, pick_kernel<kClusterSize>(1, false, heat_tables), &cfg);
   if (e != cudaSuccess) return (int)e;
   info->clusters = std::max(1, nclusters);
   info->cluster_size = kClusterSize;
@@ -779,14 +816,16 @@ void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int
 static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
 
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
-  pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles, kFaces), stream>>>(p);
+  const bool heat = p.phiheat != nullptr && p.coldens_dbg == nullptr;   // the diagnostic kernels carry no heating rates
+  pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr, heat)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles, kFaces, heat), stream>>>(p);
 }
 
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_config(&cfg, attr, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl, 1), stream);
-  return (int)cudaLaunchKernelEx(&cfg, pick_kernel<kClusterSize>(lls_mode(p), p.coldens_dbg != nullptr), p);
+  const bool heat = p.phiheat != nullptr && p.coldens_dbg == nullptr;
+  cluster_config(&cfg, attr, nclusters, rt_smem_bytes(p.smem_plane_doubles_cl, 1, heat), stream);
+  return (int)cudaLaunchKernelEx(&cfg, pick_kernel<kClusterSize>(lls_mode(p), p.coldens_dbg != nullptr, heat), p);
 }
 
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,

@@ -16,6 +16,7 @@ namespace {
 constexpr int kNumFreq = 128;  // radiation_sizes.f90:13
 
 struct FreqSide {
+  double hnu[kNumFreq + 1];     // hplanck*(frequency-ion_freq_HI), radiation_tables.F90:482-487
   double sed[kNumFreq + 1];     // BB_SED(i_freq)
   double cs[kNumFreq + 1];      // cross_section_freq_dependence
   double wgt[kNumFreq + 1];     // romw(:,7)
@@ -24,12 +25,14 @@ struct FreqSide {
 
 __constant__ FreqSide c_freq;
 
-__global__ void photo_table_kernel(double* thick, double* thin, double minlogtau, double dlogtau) {
+// heat_thick / heat_thin may be null (isothermal)
+__global__ void photo_table_kernel(double* thick, double* thin, double* heat_thick, double* heat_thin, double minlogtau,
+                                   double dlogtau) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it > kNumTau) return;
   // tau(0)=0 ; tau(i)=10.0**(minlogtau+dlogtau*real(i-1))  (radiation_tables.F90:148-155)
   const double tau = (it == 0) ? 0.0 : pow(10.0, minlogtau + dlogtau * (double)(it - 1));
-  double a_thick = 0.0, a_thin = 0.0;
+  double a_thick = 0.0, a_thin = 0.0, h_thick = 0.0, h_thin = 0.0;
   for (int i = 0; i <= kNumFreq; ++i) {
     const double x = tau * c_freq.cs[i];
     double f_thick = 0.0, f_thin = 0.0;
@@ -40,9 +43,14 @@ __global__ void photo_table_kernel(double* thick, double* thin, double minlogtau
     }
     a_thick = a_thick + f_thick * c_freq.delta_freq * c_freq.wgt[i];
     a_thin = a_thin + f_thin * c_freq.delta_freq * c_freq.wgt[i];
+    // fill_heating_integrands_HI + make_heat_tables_HI (radiation_tables.F90:471-509, 547-565)
+    h_thick = h_thick + (c_freq.hnu[i] * f_thick) * c_freq.delta_freq * c_freq.wgt[i];
+    h_thin = h_thin + (c_freq.hnu[i] * f_thin) * c_freq.delta_freq * c_freq.wgt[i];
   }
   thick[it] = a_thick;
   thin[it] = a_thin;
+  if (heat_thick) heat_thick[it] = h_thick;
+  if (heat_thin) heat_thin[it] = h_thin;
 }
 
 // Romberg weights for 2**pmax intervals: superposition of the Richardson-extrapolated
@@ -73,8 +81,8 @@ void romberg_weights(int pmax, std::vector<double>& w) {
 
 }  // namespace
 
-int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin, cudaStream_t stream,
-                           double* S_star_unscaled_out) {
+int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin, double* d_heat_thick,
+                           double* d_heat_thin, cudaStream_t stream, double* S_star_unscaled_out) {
   std::vector<double> w;
   romberg_weights(7, w);
   const double h_over_kT = sp.hplanck / (sp.k_B * sp.T_eff);
@@ -103,10 +111,12 @@ int build_blackbody_tables(const SedParams& sp, double* d_thick, double* d_thin,
                     ? 4.0 * sp.pi * R_star2 * sp.two_pi_over_c_square * f * f / (std::exp(f * h_over_kT) - 1.0)
                     : 0.0;
     fs.wgt[i] = w[i];
+    fs.hnu[i] = sp.hplanck * (f - sp.freq_min);   // freq_min = ion_freq_HI (radiation_sizes.f90:61)
   }
   cudaError_t e = cudaMemcpyToSymbolAsync(c_freq, &fs, sizeof(fs), 0, cudaMemcpyHostToDevice, stream);
   if (e != cudaSuccess) return (int)e;
-  photo_table_kernel<<<(kTableLen + 127) / 128, 128, 0, stream>>>(d_thick, d_thin, sp.minlogtau, sp.dlogtau);
+  photo_table_kernel<<<(kTableLen + 127) / 128, 128, 0, stream>>>(d_thick, d_thin, d_heat_thick, d_heat_thin, sp.minlogtau,
+                                                                  sp.dlogtau);
   e = cudaStreamSynchronize(stream);  // fs lives on this stack frame
   return (int)e;
 }

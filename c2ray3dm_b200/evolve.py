@@ -106,6 +106,42 @@ class Evolve:
         thin = np.ascontiguousarray(thin, dtype=np.float64)
         self._ck(self.L.c2b_set_tables(self.h, _dp(thick), _dp(thin), thick.size), "c2b_set_tables")
 
+    # ---- non-isothermal inputs (Evolve(..., isothermal=0)) -------------------------------------------
+    def set_heat_tables(self, heat_thick, heat_thin):
+        a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (heat_thick, heat_thin))
+        self._ck(self.L.c2b_set_heat_tables(self.h, _dp(a), _dp(b), a.size), "c2b_set_heat_tables")
+
+    def heat_tables(self):
+        """stellar_heat_thick_table / ..thin.. as the device holds them (rad_ini builds them when not isothermal)"""
+        a, b = np.zeros(_lib.NUMTAU + 1), np.zeros(_lib.NUMTAU + 1)
+        self._ck(self.L.c2b_get_heat_tables(self.h, _dp(a), _dp(b)), "c2b_get_heat_tables")
+        return a, b
+
+    def set_cooling_table(self, log10_temp, log10_cool):
+        """the 61 rows of tables/corocool.tab (cooling.f90:62-90)"""
+        a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (log10_temp, log10_cool))
+        self._ck(self.L.c2b_set_cooling_table(self.h, _dp(a), _dp(b), a.size), "c2b_set_cooling_table")
+
+    def set_redshift(self, zred):
+        self._ck(self.L.c2b_set_redshift(self.h, float(zred)), "c2b_set_redshift")
+
+    def set_temperature_grid(self, tg):
+        a = np.ascontiguousarray(tg, dtype=np.float32).reshape(-1)
+        if a.size != 3 * self.ncell:
+            raise C2RayError("temperature_grid size mismatch (3 values per cell)")
+        self._ck(self.L.c2b_set_temperature_grid(self.h, _fp(a)), "c2b_set_temperature_grid")
+
+    @property
+    def temperature_grid(self):
+        """(n3, n2, n1, 3) float32: current, average, intermed (temperature_module.F90:21-25)"""
+        out = np.empty(3 * self.ncell, dtype=np.float32)
+        self._ck(self.L.c2b_get_temperature_grid(self.h, _fp(out)), "c2b_get_temperature_grid")
+        return out.reshape(self.shape + (3,))
+
+    @property
+    def phiheat_grid(self):
+        return self._get("c2b_get_phiheat")
+
     def set_density(self, ndens):
         a = np.ascontiguousarray(ndens, dtype=np.float32).reshape(-1)
         if a.size != self.ncell:

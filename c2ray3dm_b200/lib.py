@@ -23,7 +23,9 @@ class Config(C.Structure):
                [(n, C.c_double) for n in
                 "epsilon convergence_fraction minimum_fractional_change minimum_fraction_of_atoms "
                 "loss_fraction max_coldensh tau_photo_limit minlogtau dlogtau sigma_HI pi sqrt2 sqrt3 "
-                "bh00 albpow colh0 temph0 abu_c".split()]
+                "bh00 albpow colh0 temph0 abu_c "
+                "k_B gamma1 minitemp relative_denergy tau_heat_limit H0 Omega0".split()] + \
+               [("cosmological", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class PhotonStats(C.Structure):
@@ -70,7 +72,9 @@ c2b_set_lls_grid c2b_set_lls_rmax c2b_set_temperature c2b_set_sources c2b_set_xh
 c2b_begin_step c2b_pass_all_sources c2b_global_pass c2b_end_step c2b_get_xh c2b_get_xh_av
 c2b_get_xh_intermed c2b_get_phih c2b_get_phih_f32 c2b_get_source_nbox c2b_get_source_loss
 c2b_get_iter_state c2b_set_iter_state c2b_dev_ptr c2b_synchronize c2b_trace_source_debug
-c2b_measure_dfma_rate c2b_save_xh_dev c2b_restore_xh_dev""".split()
+c2b_measure_dfma_rate c2b_save_xh_dev c2b_restore_xh_dev
+c2b_set_heat_tables c2b_get_heat_tables c2b_set_cooling_table c2b_set_redshift c2b_set_temperature_grid
+c2b_get_temperature_grid c2b_get_phiheat c2b_get_iter_state_thermal c2b_set_iter_state_thermal""".split()
 
 _lib = None
 
@@ -125,6 +129,15 @@ def load():
     L.c2b_dev_ptr.restype = vp
     L.c2b_synchronize.argtypes = [vp]
     L.c2b_save_xh_dev.argtypes = [vp]
+    L.c2b_set_heat_tables.argtypes = [vp, dp, dp, C.c_int32]
+    L.c2b_get_heat_tables.argtypes = [vp, dp, dp]
+    L.c2b_set_cooling_table.argtypes = [vp, dp, dp, C.c_int32]
+    L.c2b_set_redshift.argtypes = [vp, C.c_double]
+    L.c2b_set_temperature_grid.argtypes = [vp, fp]
+    L.c2b_get_temperature_grid.argtypes = [vp, fp]
+    L.c2b_get_phiheat.argtypes = [vp, dp]
+    L.c2b_get_iter_state_thermal.argtypes = [vp, dp, fp]
+    L.c2b_set_iter_state_thermal.argtypes = [vp, dp, fp]
     L.c2b_restore_xh_dev.argtypes = [vp]
     L.c2b_trace_source_debug.argtypes = [vp, C.c_int32, dp, dp, ip, dp]
     L.c2b_measure_dfma_rate.argtypes = [vp, dp]

@@ -44,7 +44,8 @@ typedef struct c2b_config {
   int32_t mesh[3];            /* sizes.f90:33 */
   int32_t device;             /* CUDA device ordinal */
   int32_t rank, nranks;       /* my_mpi: rank, npr */
-  int32_t isothermal;         /* c2ray_parameters.f90:28 -- only 1 is implemented */
+  int32_t isothermal;         /* c2ray_parameters.f90:28; 0 = heating and cooling (thermal.f90), needs the heat
+                                 tables, a cooling table, the redshift and a temperature grid (below) */
   int32_t type_of_clumping;   /* :75   1,2 = scalar; 3,4,5 = float32 grid */
   int32_t use_LLS;            /* :80 */
   int32_t type_of_LLS;        /* :87   1 = scalar, 2 = float32 grid, 3 = R_max barrier */
@@ -65,6 +66,15 @@ typedef struct c2b_config {
   double sqrt2, sqrt3;               /* column_density.f90:52-53 */
   double bh00, albpow, colh0, temph0;/* cgsconstants.f90:64-86 */
   double abu_c;                      /* abundances.f90:26 */
+  /* non-isothermal path (isothermal == 0): thermal.f90, cooling.f90, heat_lookuptable, cosmo_cool */
+  double k_B;                        /* cgsconstants.f90:34 */
+  double gamma1;                     /* atomic.f90:23-25: 5/3 - 1 */
+  double minitemp;                   /* c2ray_parameters.f90:108 */
+  double relative_denergy;           /* :110 */
+  double tau_heat_limit;             /* radiation_photoionrates.F90:333 */
+  double H0, Omega0;                 /* cosmoparms.f90:30,41 (cosmo_cool, cosmology.F90:198-225) */
+  int32_t cosmological;              /* c2ray_parameters.f90:105 */
+  int32_t reserved1;
 } c2b_config;
 
 /* photonstatistics.F90:41-55 module variables + the report line of :254-281 */
@@ -145,6 +155,19 @@ int c2b_set_sources(c2b_handle *h, int32_t NumSrc, const int32_t *srcpos /* 3 x 
                     const double *NormFlux_stellar /* NumSrc; element 0 = source 1 */,
                     double S_star);                                     /* sourceprops.F90:56-63 */
 int c2b_set_xh(c2b_handle *h, const double *xh);                        /* ionfractions_module.F90:22 */
+/* ---- non-isothermal inputs (isothermal == 0) ----------------------------------------------- */
+/* stellar_heat_thick_table(0:NumTau,1), ..thin.. (radiation_tables.F90:82-83); c2b_rad_ini_blackbody builds them
+ * itself when the handle is not isothermal, c2b_get_heat_tables reads them back */
+int c2b_set_heat_tables(c2b_handle *h, const double *heat_thick, const double *heat_thin, int32_t n);
+int c2b_get_heat_tables(c2b_handle *h, double *heat_thick, double *heat_thin);
+/* the 61 rows (log10 T, log10 Lambda) of tables/corocool.tab as setup_cool reads them (cooling.f90:62-90) */
+int c2b_set_cooling_table(c2b_handle *h, const double *log10_temp, const double *log10_cool, int32_t n /* 61 */);
+int c2b_set_redshift(c2b_handle *h, double zred);                       /* cosmology.F90:42 (cosmo_cool) */
+/* temperature_grid(mesh)%(current,average,intermed), default real (temperature_module.F90:21-35): 3 floats per
+ * cell, cell index i fastest.  c2b_set_temperature(temper_val) fills all three with temper_val
+ * (temperature_array_init, :44-67). */
+int c2b_set_temperature_grid(c2b_handle *h, const float *temperature_grid);
+int c2b_get_temperature_grid(c2b_handle *h, float *temperature_grid);
 
 /* ---- the hot path ------------------------------------------------------------------------ */
 /* coarse: evolve3D(time,dt,restart) evolve.F90:83-281; restart must be 0 unless
@@ -163,6 +186,7 @@ int c2b_get_xh_av(c2b_handle *h, double *xh_av);
 int c2b_get_xh_intermed(c2b_handle *h, double *xh_intermed);
 int c2b_get_phih(c2b_handle *h, double *phih_grid);
 int c2b_get_phih_f32(c2b_handle *h, float *phih_grid_si);  /* real(phih_grid,si), output.F90:359 */
+int c2b_get_phiheat(c2b_handle *h, double *phiheat_grid);   /* evolve_data.F90:42 (non-isothermal) */
 int c2b_get_source_nbox(c2b_handle *h, int32_t *nbox /* NumSrc; 0 for sources of other ranks */);
 int c2b_get_source_loss(c2b_handle *h, double *loss /* NumSrc */);
 /* iteration dump / restart (evolve.F90:285-426): niter, photon_loss_all, phih, xh_av, xh_intermed */
@@ -170,6 +194,10 @@ int c2b_get_iter_state(c2b_handle *h, int32_t *niter, double *photon_loss_all, d
                        double *xh_av, double *xh_intermed);
 int c2b_set_iter_state(c2b_handle *h, int32_t niter, double photon_loss_all, const double *phih_grid,
                        const double *xh_av, const double *xh_intermed);
+
+/* the two extra records of a non-isothermal dump: phiheat_grid | temperature_grid (evolve.F90:314-317) */
+int c2b_get_iter_state_thermal(c2b_handle *h, double *phiheat_grid, float *temperature_grid);
+int c2b_set_iter_state_thermal(c2b_handle *h, const double *phiheat_grid, const float *temperature_grid);
 
 /* ---- device-side access for harnesses that already hold data in HBM (bench, tests) -------- */
 void *c2b_dev_ptr(c2b_handle *h, const char *name); /* "ndens","xh","xh_av","xh_intermed","phih" */

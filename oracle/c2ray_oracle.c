@@ -47,6 +47,12 @@ static const int K_subboxsize = 5;                            /* :54 */
 static const int K_max_subbox = 1000;                         /* :61 */
 static const double K_max_coldensh = F32(2e19f);              /* evolve_point.F90:95 */
 static const double K_tau_photo_limit = F32(1.0e-7f);         /* radiation_photoionrates.F90:244 */
+static const double K_tau_heat_limit = F32(1.0e-4f);         /* radiation_photoionrates.F90:333 */
+static const double K_minitemp = F32(1.0f);                   /* c2ray_parameters.f90:108 */
+static const double K_relative_denergy = F32(0.1f);           /* :110 */
+static const double K_gamma1 = 5.0 / 3.0 - 1.0;               /* atomic.f90:23-25 */
+static const double K_Omega0 = F32(0.27f);                    /* cosmoparms.f90:30 */
+static const double K_h = F32(0.7f);                          /* :28 */
 static const double K_minlogtau = -20.0;                      /* radiation_tables.F90:45 */
 static const double K_maxlogtau = 4.0;                        /* :46 */
 
@@ -63,8 +69,10 @@ static double K_ion_freq_HI(void) { return K_ev2fr() * K_eth0; }               /
 static double K_ion_freq_HeII(void) { return K_ev2fr() * K_ethe1; }            /* :33 */
 static double K_two_pi_over_c_square(void) { return F32(2.0f) * K_pi / (K_c * K_c); } /* cgsconstants.f90:61 */
 static double K_dlogtau(void) { return (K_maxlogtau - K_minlogtau) / (double)(float)ORC_NUMTAU; } /* radiation_tables.F90:47 */
+static double K_H0(void);
 static double K_R_SOLAR(void) { return F32(6.9599e10f); }                      /* cgsastroconstants.f90:23 */
 static double K_Mpc(void) { return F32(1e6f) * F32(3.086e18f); }               /* :29-31 */
+static double K_H0(void) { return K_h * F32(100.0f) * F32(1e5f) / K_Mpc(); }   /* cosmoparms.f90:41 */
 
 void orc_get_constants(orc_constants *c) {
   memset(c, 0, sizeof(*c));
@@ -162,7 +170,14 @@ static void romberg_free(romberg_t *R, int pmax) {
 /* ------------------------------------------------------------------------------------------ */
 /* rad_ini: radiation_tables.F90:95-126 and callees                                             */
 /* ------------------------------------------------------------------------------------------ */
-void orc_rad_ini(double *thick, double *thin, orc_rad_diag *diag) {
+static void rad_ini_impl(double *thick, double *thin, double *heat_thick, double *heat_thin, orc_rad_diag *diag);
+void orc_rad_ini(double *thick, double *thin, orc_rad_diag *diag) { rad_ini_impl(thick, thin, NULL, NULL, diag); }
+/* rad_ini with isothermal=.false.: also stellar_heat_thick_table / stellar_heat_thin_table
+ * (fill_heating_integrands_HI radiation_tables.F90:471-509, make_heat_tables_HI :547-565) */
+void orc_rad_ini_heat(double *thick, double *thin, double *heat_thick, double *heat_thin) {
+  rad_ini_impl(thick, thin, heat_thick, heat_thin, NULL);
+}
+static void rad_ini_impl(double *thick, double *thin, double *heat_thick, double *heat_thin, orc_rad_diag *diag) {
   const int NF = ORC_NUMFREQ, NT = ORC_NUMTAU;
   const double pi = K_pi;
   const double ion_freq_HI = K_ion_freq_HI();
@@ -234,7 +249,7 @@ void orc_rad_ini(double *thick, double *thin, orc_rad_diag *diag) {
       sed[i] = 0.0;
   }
   for (int it = 0; it <= NT; ++it) { /* fill_photo_integrands :361-430 + make_photo_tables :524-543 */
-    double a_thick = 0.0, a_thin = 0.0;
+    double a_thick = 0.0, a_thin = 0.0, h_thick = 0.0, h_thin = 0.0;
     for (int i = 0; i <= NF; ++i) {
       double f_thick, f_thin;
       if (tau[it] * cs[i] < F32(700.0f)) {
@@ -247,9 +262,14 @@ void orc_rad_ini(double *thick, double *thin, orc_rad_diag *diag) {
       /* vector_romberg romberg.f90:158-187 with vector_weight = delta_freq */
       a_thick = a_thick + f_thick * delta_freq * romw7[i];
       a_thin = a_thin + f_thin * delta_freq * romw7[i];
+      /* heating integrands :482-487: hplanck*(frequency-ion_freq_HI)*photo integrand */
+      h_thick = h_thick + (K_hplanck * (frequency[i] - ion_freq_HI) * f_thick) * delta_freq * romw7[i];
+      h_thin = h_thin + (K_hplanck * (frequency[i] - ion_freq_HI) * f_thin) * delta_freq * romw7[i];
     }
     thick[it] = a_thick;
     thin[it] = a_thin;
+    if (heat_thick) heat_thick[it] = h_thick;
+    if (heat_thin) heat_thin[it] = h_thin;
   }
   if (diag) {
     diag->S_star_unscaled = S_star_unscaled;
@@ -297,6 +317,14 @@ struct orc_state {
   int last_l[3], last_r[3], lastpos_l[3], lastpos_r[3];
   double photon_loss_src_thread;
   int64_t updates;
+  /* non-isothermal path (c2ray_parameters.f90:28 isothermal=.false.) */
+  int isothermal;                     /* 1 by default, as shipped */
+  int cosmological;                   /* c2ray_parameters.f90:105 */
+  double zred;                        /* cosmology.F90:42, current redshift (cosmo_cool) */
+  double heat_thick[ORC_NUMTAU + 1], heat_thin[ORC_NUMTAU + 1]; /* stellar_heat_*_table(:,1) */
+  double *phiheat_grid;               /* evolve_data.F90:42 */
+  float *temperature_grid;            /* temperature_module.F90:21-35: (current, average, intermed) per cell */
+  double cie_cool[61], cool_mintemp, cool_dtemp; /* cooling.f90:29-32 */
   /* iteration dump (evolve.F90:285-324) kept in memory */
   int dump_at_iter, have_dump, dump_niter;
   double dump_photon_loss_all;
@@ -323,6 +351,8 @@ orc_state *orc_create(int m1, int m2, int m3) {
   s->loss_fraction = 1e-2;
   s->npr = 1;
   s->nthreads = 1;
+  s->isothermal = 1;
+  s->cosmological = 1;
   return s;
 }
 void orc_destroy(orc_state *s) {
@@ -331,6 +361,7 @@ void orc_destroy(orc_state *s) {
   free(s->coldensh_out); free(s->clumping_grid); free(s->LLS_grid); free(s->srcpos);
   free(s->NormFlux_stellar);
   free(s->dump_phih); free(s->dump_xh_av); free(s->dump_xh_intermed);
+  free(s->phiheat_grid); free(s->temperature_grid);
   free(s);
 }
 void orc_set_tables(orc_state *s, const double *thick, const double *thin) {
@@ -384,6 +415,34 @@ void orc_set_loss_fraction(orc_state *s, double lf) { s->loss_fraction = lf; }
 void orc_set_walk_order(orc_state *s, int order) { s->walk_order = order; }
 void orc_set_rank(orc_state *s, int rank, int npr) { s->rank = rank; s->npr = npr; }
 void orc_set_threads(orc_state *s, int n) { s->nthreads = n < 1 ? 1 : n; }
+
+/* ---- non-isothermal inputs ------------------------------------------------------------------ */
+/* isothermal=.false. (c2ray_parameters.f90:28): allocates phiheat_grid (evolve_data.F90:77) and
+ * temperature_grid, filled with temper_val (temperature_array_init temperature_module.F90:44-67) */
+void orc_set_isothermal(orc_state *s, int isothermal) {
+  s->isothermal = isothermal ? 1 : 0;
+  if (!s->isothermal && !s->phiheat_grid) {
+    s->phiheat_grid = (double *)calloc(s->ncell, sizeof(double));
+    s->temperature_grid = (float *)malloc(3 * s->ncell * sizeof(float));
+    for (size_t p = 0; p < 3 * s->ncell; ++p) s->temperature_grid[p] = (float)s->temper_val;
+  }
+}
+void orc_set_heat_tables(orc_state *s, const double *heat_thick, const double *heat_thin) {
+  memcpy(s->heat_thick, heat_thick, sizeof(s->heat_thick));
+  memcpy(s->heat_thin, heat_thin, sizeof(s->heat_thin));
+}
+/* setup_cool cooling.f90:62-90: 61 rows (log10 T, log10 Lambda) of tables/corocool.tab */
+void orc_set_cooling_table(orc_state *s, const double *log10_temp, const double *log10_cool) {
+  s->cool_mintemp = log10_temp[0];
+  s->cool_dtemp = log10_temp[1] - log10_temp[0];
+  for (int i = 0; i < 61; ++i) s->cie_cool[i] = pow(10.0, log10_cool[i]);
+}
+void orc_set_redshift(orc_state *s, double zred, int cosmological) {
+  s->zred = zred;
+  s->cosmological = cosmological;
+}
+float *orc_temperature_grid(orc_state *s) { return s->temperature_grid; }
+double *orc_phiheat(orc_state *s) { return s->phiheat_grid; }
 double *orc_xh(orc_state *s) { return s->xh; }
 double *orc_xh_av(orc_state *s) { return s->xh_av; }
 double *orc_xh_intermed(orc_state *s) { return s->xh_intermed; }
@@ -535,12 +594,12 @@ static inline double read_table(const double *table, const tablepos *p) {
   return table[p->ipos] + (table[p->ipos_p1] - table[p->ipos]) * p->residual;
 }
 
-typedef struct { double photo_cell_HI, photo_in, photo_out; } photrates;
+typedef struct { double photo_cell_HI, photo_in, photo_out, heat; } photrates;
 
 /* photoion_rates :71-179 with photo_lookuptable :233-317, table_type "B", isothermal */
 static inline photrates photoion_rates(const orc_state *s, double colum_in_HI, double colum_out_HI,
                                        double vol, double NFlux) {
-  photrates phi = {0.0, 0.0, 0.0}; /* set_photrates_to_zero :442-450 */
+  photrates phi = {0.0, 0.0, 0.0, 0.0}; /* set_photrates_to_zero :442-450 */
   const double sigma_HI = K_sigma_HI(); /* radiation_sizes.f90:77 */
   double tau_in = colum_in_HI * sigma_HI;
   double tau_out = colum_out_HI * sigma_HI;
@@ -561,6 +620,19 @@ static inline photrates photoion_rates(const orc_state *s, double colum_in_HI, d
     phi.photo_out = 0.0 + (0.0 + phi_photo_out_all);
     phi.photo_cell_HI = 0.0 + (0.0 + phi_photo_all / vol);
   }
+  if (!s->isothermal && NFlux > 0.0) { /* :140-165 -> heat_lookuptable :323-417, table_type "B", one sub-band */
+    double tau_cell_HI = (colum_out_HI - colum_in_HI) * sigma_HI; /* :144-146 */
+    double phi_heat_in_HI = NFlux * read_table(s->heat_thick, &pin);
+    double phi_heat_HI;
+    if (fabs(tau_out - tau_in) > K_tau_heat_limit) {
+      double phi_heat_out_HI = NFlux * read_table(s->heat_thick, &pout);
+      phi_heat_HI = (phi_heat_in_HI - phi_heat_out_HI) / vol;
+    } else {
+      phi_heat_HI = NFlux * tau_cell_HI * read_table(s->heat_thin, &pin);
+      phi_heat_HI = phi_heat_HI / vol;
+    }
+    phi.heat = 0.0 + (0.0 + phi_heat_HI); /* f_heat = f_heat + df_heat ; phi = phi + ... */
+  }
   return phi;
 }
 
@@ -579,6 +651,7 @@ typedef struct {
   const orc_state *s;
   double *coldensh_out; /* may be thread-private */
   double *phih_grid;    /* may be thread-private */
+  double *phiheat_grid; /* may be thread-private; NULL when isothermal */
   int last_l[3], last_r[3];
   double photon_loss_src_thread;
   int64_t updates;
@@ -634,8 +707,10 @@ static void evolve0D(walk_ctx *w, const int rtpos[3], int ns) {
       phi.photo_cell_HI = 0.0;
       phi.photo_in = 0.0;
       phi.photo_out = 0.0;
+      phi.heat = 0.0;
     }
     w->phih_grid[p] = w->phih_grid[p] + phi.photo_cell_HI; /* :283-284 */
+    if (!s->isothermal) w->phiheat_grid[p] = w->phiheat_grid[p] + phi.heat; /* :285-286 */
     if (rtpos[0] == w->last_l[0] || rtpos[1] == w->last_l[1] || rtpos[2] == w->last_l[2] ||
         rtpos[0] == w->last_r[0] || rtpos[1] == w->last_r[1] || rtpos[2] == w->last_r[2]) { /* :290-295 */
       w->photon_loss_src_thread = w->photon_loss_src_thread + phi.photo_out * s->vol / vol_ph;
@@ -721,12 +796,13 @@ static void sweep_shells_scrambled(walk_ctx *w, int ns) {
 }
 
 /* do_source evolve_source.F90:58-221 */
-static void do_source(const orc_state *s, double *coldensh_out, double *phih_grid, int ns,
+static void do_source(const orc_state *s, double *coldensh_out, double *phih_grid, double *phiheat_grid, int ns,
                       orc_source_report *rep) {
   walk_ctx w;
   w.s = s;
   w.coldensh_out = coldensh_out;
   w.phih_grid = phih_grid;
+  w.phiheat_grid = phiheat_grid;
   w.updates = 0;
   const int *src = &s->srcpos[3 * (ns - 1)];
   int lastpos_l[3], lastpos_r[3];
@@ -780,13 +856,14 @@ static void do_source(const orc_state *s, double *coldensh_out, double *phih_gri
 }
 
 void orc_do_source(orc_state *s, int ns, orc_source_report *rep) {
-  do_source(s, s->coldensh_out, s->phih_grid, ns, rep);
+  do_source(s, s->coldensh_out, s->phih_grid, s->phiheat_grid, ns, rep);
   s->photon_loss = s->photon_loss + rep->photon_loss_src; /* :216 */
 }
 
 /* evolve.F90:430-440 */
 void orc_set_rates_to_zero(orc_state *s) {
   memset(s->phih_grid, 0, s->ncell * sizeof(double));
+  if (!s->isothermal) memset(s->phiheat_grid, 0, s->ncell * sizeof(double)); /* :435 */
   s->photon_loss = 0.0;
   s->LLS_loss = 0.0;
 }
@@ -801,7 +878,7 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
   if (s->nthreads <= 1 || mine <= 1) {
     for (int ns1 = 1 + s->rank; ns1 <= s->NumSrc; ns1 += s->npr) {
       orc_source_report r;
-      do_source(s, s->coldensh_out, s->phih_grid, ns1, &r);
+      do_source(s, s->coldensh_out, s->phih_grid, s->phiheat_grid, ns1, &r);
       photon_loss = photon_loss + r.photon_loss_src; /* evolve_source.F90:216 */
       sum_nbox += r.nbox;                            /* :219 */
       updates += r.updates;
@@ -809,6 +886,7 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
   } else {
     int T = s->nthreads < mine ? s->nthreads : mine;
     double **priv = (double **)calloc((size_t)T, sizeof(double *));
+    double **privh = (double **)calloc((size_t)T, sizeof(double *));   /* phiheat_grid of the emulated rank */
     double *ploss = (double *)calloc((size_t)T, sizeof(double));
     int64_t *pnbox = (int64_t *)calloc((size_t)T, sizeof(int64_t));
     int64_t *pupd = (int64_t *)calloc((size_t)T, sizeof(int64_t));
@@ -823,13 +901,15 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
 #endif
       double *cd = (double *)malloc(s->ncell * sizeof(double));
       double *ph = (double *)calloc(s->ncell, sizeof(double));
+      double *phh = s->isothermal ? NULL : (double *)calloc(s->ncell, sizeof(double));
       priv[t] = ph;
+      privh[t] = phh;
       /* sources of this rank, dealt round-robin to the emulated ranks */
       int cnt = 0;
       for (int ns1 = 1 + s->rank; ns1 <= s->NumSrc; ns1 += s->npr, ++cnt) {
         if (cnt % T != t) continue;
         orc_source_report r;
-        do_source(s, cd, ph, ns1, &r);
+        do_source(s, cd, ph, phh, ns1, &r);
         ploss[t] += r.photon_loss_src;
         pnbox[t] += r.nbox;
         pupd[t] += r.updates;
@@ -842,12 +922,16 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
     for (int t = 0; t < T; ++t) {
       if (!priv[t]) continue;
       for (size_t p = 0; p < s->ncell; ++p) s->phih_grid[p] += priv[t][p];
+      if (privh[t]) { /* evolve.F90:604-609 */
+        for (size_t p = 0; p < s->ncell; ++p) s->phiheat_grid[p] += privh[t][p];
+        free(privh[t]);
+      }
       photon_loss += ploss[t];
       sum_nbox += pnbox[t];
       updates += pupd[t];
       free(priv[t]);
     }
-    free(priv); free(ploss); free(pnbox); free(pupd);
+    free(priv); free(privh); free(ploss); free(pnbox); free(pupd);
   }
   s->photon_loss = s->photon_loss + photon_loss;
   rep->photon_loss_all = s->photon_loss; /* photon_loss_all(:)=photon_loss(:) :485 */
@@ -891,7 +975,66 @@ void orc_doric(const orc_state *s, double dt, double temp0, double rhe, double r
   doric(dt, temp0, rhe, rhh, xfh, xfh_av, phih, clumping);
 }
 
-/* evolve0D_global evolve_point.F90:305-406 with do_chemistry :410-555 (local=.false., isothermal) */
+/* coolin cooling.f90:38-59 */
+static inline double coolin(const orc_state *s, double nucldens, double eldens, double temp0) {
+  double tpos = (log10(temp0) - s->cool_mintemp) / s->cool_dtemp + 1.0;
+  int itpos = (int)tpos;
+  if (itpos < 1) itpos = 1;
+  if (itpos > 61 - 1) itpos = 61 - 1;
+  double dtpos = tpos - (double)(float)itpos;
+  int itpos1 = itpos + 1 < 61 ? itpos + 1 : 61;
+  return nucldens * eldens * (s->cie_cool[itpos - 1] + (s->cie_cool[itpos1 - 1] - s->cie_cool[itpos - 1]) * dtpos);
+}
+
+/* cosmo_cool cosmology.F90:198-225 */
+static inline double cosmo_cool(const orc_state *s, double e_int) {
+  double zred = s->zred;
+  double dzdt = K_H0() * (F32(1.f) + zred) * sqrt(K_Omega0 * pow(F32(1.f) + zred, 3) + F32(1.f) - K_Omega0);
+  return e_int * F32(2.0f) / (F32(1.0f) + zred) * dzdt;
+}
+
+/* thermal thermal.f90:22-176; final/average are left untouched when initial_temperature <= minitemp */
+static void thermal(const orc_state *s, double dt, double initial_temperature, double *final_temperature,
+                    double *average_temperature, double ndens_electron, double ndens_atom, const double h[2],
+                    const double h_old[2], const double h_av[2], double heat) {
+  /* temper2pressr tped.f90:41-53: (ndens+eldens)*k_B*temper */
+  double internal_energy =
+      (ndens_atom + electrondens(ndens_atom, h_old)) * K_k_B * initial_temperature / K_gamma1;
+  double heating = heat;
+  double cosmo_cool_rate = s->cosmological ? cosmo_cool(s, internal_energy) : 0.0;
+  if (initial_temperature > K_minitemp) {
+    double cumulative_time = 0.0;
+    int i_heating = 0;
+    double avg = 0.0;
+    double intermediate_temperature = initial_temperature;
+    for (;;) {
+      i_heating = i_heating + 1;
+      double cooling = coolin(s, ndens_atom, ndens_electron, intermediate_temperature) + cosmo_cool_rate;
+      double thermal_rate = fmax(1e-50, fabs(cooling - heating));
+      double thermal_timescale = internal_energy / fabs(thermal_rate);
+      double dt_thermal = K_relative_denergy * thermal_timescale;
+      double dt_ODE = fmin(dt_thermal, dt - cumulative_time);
+      internal_energy = internal_energy + dt_ODE * (heating - cooling);
+      avg = avg + F32(0.5f) * intermediate_temperature * dt_ODE;
+      /* pressr2temper tped.f90:58-70: pressr/(k_B*(ndens+eldens)) */
+      intermediate_temperature = internal_energy * K_gamma1 / (K_k_B * (ndens_atom + electrondens(ndens_atom, h_av)));
+      avg = avg + F32(0.5f) * intermediate_temperature * dt_ODE;
+      if (intermediate_temperature < K_minitemp) {
+        internal_energy = (ndens_atom + electrondens(ndens_atom, h_av)) * K_k_B * K_minitemp; /* no /gamma1, :131 */
+        intermediate_temperature = K_minitemp;
+      }
+      cumulative_time = cumulative_time + dt_ODE;
+      if (cumulative_time >= dt || fabs(cumulative_time - dt) < F32(1e-6f) * dt) break;
+      if (i_heating > 10000) break;
+    }
+    if (dt > 0.0) avg = avg / dt;
+    else avg = initial_temperature;
+    *average_temperature = avg;
+    *final_temperature = internal_energy * K_gamma1 / (K_k_B * (ndens_atom + electrondens(ndens_atom, h)));
+  }
+}
+
+/* evolve0D_global evolve_point.F90:305-406 with do_chemistry :410-555 (local=.false.) */
 static void evolve0D_global(orc_state *s, double dt, size_t p, int *conv_flag) {
   double h[2], h_old[2], h_av[2];
   h[1] = fmax(K_epsilon, s->xh_intermed[p]);
@@ -901,34 +1044,56 @@ static void evolve0D_global(orc_state *s, double dt, size_t p, int *conv_flag) {
   h_old[0] = F32(1.0f) - h_old[1];
   h_av[0] = F32(1.0f) - h_av[1];
   double ndens_p = (double)s->ndens[p];
-  double T = s->temper_val; /* get_temperature_point, isothermal (temperature_module.F90:134-151) */
+  /* get_temperature_point temperature_module.F90:134-151: (current, average, intermed) */
+  double Tstart_cur, Tstart_avg, Tstart_int;
+  if (s->isothermal) {
+    Tstart_cur = Tstart_avg = Tstart_int = s->temper_val;
+  } else {
+    Tstart_cur = (double)s->temperature_grid[3 * p];
+    Tstart_avg = (double)s->temperature_grid[3 * p + 1];
+    Tstart_int = (double)s->temperature_grid[3 * p + 2];
+  }
   double phi_cell = s->phih_grid[p];
-  /* do_chemistry */
+  double heat = s->isothermal ? 0.0 : s->phiheat_grid[p]; /* :364 */
+  /* do_chemistry: temperature_end=temperature_start */
+  double Tend_cur = Tstart_cur, Tend_avg = Tstart_avg, Tend_int = Tstart_int;
   float clumping = s->clumping;
   if (s->type_of_clumping == 3 || s->type_of_clumping == 4 || s->type_of_clumping == 5)
     clumping = s->clumping_grid[p]; /* clumping_point clumping_module.F90:106-118 */
   int nit = 0;
   for (;;) {
     nit = nit + 1;
+    double temperature_previous_iteration = Tend_cur;
     double yh0_av_old = h_av[0];
     h[0] = h_old[0];
     h[1] = h_old[1];
     double de = electrondens(ndens_p, h_av);
-    doric(dt, T, de, ndens_p, h, h_av, phi_cell, clumping);
+    /* ini_rec_colion_factors(temperature_end%average) (:491) only sets module variables doric does not use */
+    doric(dt, Tend_avg, de, ndens_p, h, h_av, phi_cell, clumping);
     de = electrondens(ndens_p, h_av);
-    (void)de;
-    /* temperature term: |current-previous|/current == 0 < minimum_fractional_change (Appendix E.8) */
-    if (fabs((h_av[0] - yh0_av_old) / h_av[0]) < K_minimum_fractional_change ||
-        h_av[0] < K_minimum_fraction_of_atoms)
+    if (!s->isothermal) /* :519-526 */
+      thermal(s, dt, Tstart_cur, &Tend_int, &Tend_avg, de, ndens_p, h, h_old, h_av, heat);
+    /* the temperature term compares temperature_end%current, which thermal never updates (Appendix E.8) */
+    if ((fabs((h_av[0] - yh0_av_old) / h_av[0]) < K_minimum_fractional_change ||
+         h_av[0] < K_minimum_fraction_of_atoms) &&
+        fabs((Tend_cur - temperature_previous_iteration) / Tend_cur) < K_minimum_fractional_change)
       break;
     if (nit > 400) break; /* :541-549 'Convergence failing (global)' */
+  }
+  /* set_temperature_point (:553, temperature_module.F90:155-169): intermed and average, as default real */
+  if (!s->isothermal) {
+    s->temperature_grid[3 * p + 2] = (float)Tend_int;
+    s->temperature_grid[3 * p + 1] = (float)Tend_avg;
   }
   /* :378-391 */
   double yh1_av_old = fmax(K_epsilon, s->xh_av[p]);
   double yh0_av_old = F32(1.0f) - yh1_av_old;
-  if (fabs(h_av[0] - yh0_av_old) > K_minimum_fractional_change &&
-      fabs((h_av[0] - yh0_av_old) / h_av[0]) > K_minimum_fractional_change &&
-      h_av[0] > K_minimum_fraction_of_atoms)
+  /* get_temperature_point again: the values just stored, rounded to default real */
+  double Tnew_avg = s->isothermal ? s->temper_val : (double)s->temperature_grid[3 * p + 1];
+  if ((fabs(h_av[0] - yh0_av_old) > K_minimum_fractional_change &&
+       fabs((h_av[0] - yh0_av_old) / h_av[0]) > K_minimum_fractional_change &&
+       h_av[0] > K_minimum_fraction_of_atoms) ||
+      (fabs((Tstart_avg - Tnew_avg) / Tnew_avg) > 1.0e-1 && fabs(Tstart_avg - Tnew_avg) > 100.0))
     *conv_flag = *conv_flag + 1;
   s->xh_intermed[p] = h[1];
   s->xh_av[p] = h_av[1];
@@ -968,8 +1133,16 @@ static void total_rates(orc_state *s, double dt, const double *xh_l) { /* :137-1
     float clumping = s->clumping;
     if (s->type_of_clumping == 3 || s->type_of_clumping == 4 || s->type_of_clumping == 5)
       clumping = s->clumping_grid[p];
-    totrec = totrec + ndens_p * yh[1] * electrondens(ndens_p, yh) * (double)clumping * K_bh00 * powT;
-    totcoll = totcoll + ndens_p * yh[0] * electrondens(ndens_p, yh) * K_colh0() * sqrtT * expT;
+    if (s->isothermal) {
+      totrec = totrec + ndens_p * yh[1] * electrondens(ndens_p, yh) * (double)clumping * K_bh00 * powT;
+      totcoll = totcoll + ndens_p * yh[0] * electrondens(ndens_p, yh) * K_colh0() * sqrtT * expT;
+    } else { /* temperature%average of the cell, photonstatistics.F90:166-176 */
+      const double Ta = (double)s->temperature_grid[3 * p + 1];
+      totrec = totrec + ndens_p * yh[1] * electrondens(ndens_p, yh) * (double)clumping * K_bh00 *
+                            pow(Ta / F32(1e4f), K_albpow);
+      totcoll = totcoll + ndens_p * yh[0] * electrondens(ndens_p, yh) * K_colh0() * sqrt(Ta) *
+                              exp(-K_temph0() / Ta);
+    }
   }
   s->totrec = totrec * s->vol * dt;
   s->totcollisions = totcoll * s->vol * dt;
@@ -1102,6 +1275,8 @@ static void evolve3D_impl(orc_state *s, double dt, int max_outer_iter, int resta
     if (conv_flag < conv_criterion ||
         (rel_change_sum_xh1 < K_convergence_fraction && rel_change_sum_xh0 < K_convergence_fraction)) { /* :212-214 */
       memcpy(s->xh, s->xh_intermed, s->ncell * sizeof(double));
+      if (!s->isothermal) /* set_final_temperature_point temperature_module.F90:173-183: current=intermed */
+        for (size_t p = 0; p < s->ncell; ++p) s->temperature_grid[3 * p] = s->temperature_grid[3 * p + 2];
       rep->converged = 1;
       break;
     } else {

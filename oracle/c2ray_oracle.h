@@ -69,6 +69,15 @@ void orc_set_rank(orc_state *s, int rank, int npr);
 /* number of OpenMP threads used by orc_pass_all_sources in source-parallel CPU-baseline mode. */
 void orc_set_threads(orc_state *s, int nthreads);
 
+/* ---- non-isothermal path (isothermal=.false.; thermal.f90, cooling.f90, heat_lookuptable) ---------- */
+void orc_rad_ini_heat(double *thick, double *thin, double *heat_thick, double *heat_thin);
+void orc_set_isothermal(orc_state *s, int isothermal);   /* after orc_set_temperature: grids start at temper_val */
+void orc_set_heat_tables(orc_state *s, const double *heat_thick, const double *heat_thin);
+void orc_set_cooling_table(orc_state *s, const double *log10_temp /*61*/, const double *log10_cool /*61*/);
+void orc_set_redshift(orc_state *s, double zred, int cosmological);   /* cosmology.F90:42, c2ray_parameters.f90:105 */
+float *orc_temperature_grid(orc_state *s);   /* 3 x ncell: (current, average, intermed) per cell */
+double *orc_phiheat(orc_state *s);
+
 double *orc_xh(orc_state *s);
 double *orc_xh_av(orc_state *s);
 double *orc_xh_intermed(orc_state *s);

@@ -120,6 +120,15 @@ def lib():
         L.orc_state_before.argtypes = [vp]
         L.orc_calculate_photon_statistics.argtypes = [vp, C.c_double, dp, dp, C.POINTER(PhotonStats)]
         L.orc_evolve3D.argtypes = [vp, C.c_double, C.c_int, C.POINTER(StepReport)]
+        L.orc_rad_ini_heat.argtypes = [dp, dp, dp, dp]
+        L.orc_set_isothermal.argtypes = [vp, C.c_int]
+        L.orc_set_heat_tables.argtypes = [vp, dp, dp]
+        L.orc_set_cooling_table.argtypes = [vp, dp, dp]
+        L.orc_set_redshift.argtypes = [vp, C.c_double, C.c_int]
+        L.orc_temperature_grid.restype = fp
+        L.orc_temperature_grid.argtypes = [vp]
+        L.orc_phiheat.restype = dp
+        L.orc_phiheat.argtypes = [vp]
         L.orc_set_dump_iteration.argtypes = [vp, C.c_int]
         L.orc_get_dump.argtypes = [vp, C.POINTER(C.c_int), dp, dp, dp, dp]
         L.orc_evolve3D_restart.argtypes = [vp, C.c_double, C.c_int, C.c_int, C.c_double, dp, dp, dp,
@@ -147,6 +156,13 @@ def rad_ini():
         lib().orc_rad_ini(_dp(thick), _dp(thin), C.byref(d))
         _tables_cache = (thick, thin, d)
     return _tables_cache
+
+
+def rad_ini_heat():
+    """rad_ini with isothermal=.false.: (thick, thin, heat_thick, heat_thin)"""
+    t = [np.zeros(NUMTAU + 1) for _ in range(4)]
+    lib().orc_rad_ini_heat(_dp(t[0]), _dp(t[1]), _dp(t[2]), _dp(t[3]))
+    return tuple(t)
 
 
 def _dp(a):
@@ -310,6 +326,35 @@ class Oracle:
         r = StepReport()
         self.L.orc_evolve3D(self.h, float(dt), int(max_outer_iter), C.byref(r))
         return r
+
+    # ---- non-isothermal path ------------------------------------------------------------------------
+    def set_isothermal(self, isothermal):
+        """isothermal=.false. allocates phiheat_grid and temperature_grid (filled with temper_val)"""
+        self.L.orc_set_isothermal(self.h, int(bool(isothermal)))
+
+    def set_heat_tables(self, heat_thick, heat_thin):
+        a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (heat_thick, heat_thin))
+        self.L.orc_set_heat_tables(self.h, _dp(a), _dp(b))
+
+    def set_cooling_table(self, log10_temp, log10_cool):
+        """the 61 rows of tables/corocool.tab (cooling.f90:62-90)"""
+        a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (log10_temp, log10_cool))
+        assert a.size == 61 and b.size == 61
+        self.L.orc_set_cooling_table(self.h, _dp(a), _dp(b))
+
+    def set_redshift(self, zred, cosmological=True):
+        self.L.orc_set_redshift(self.h, float(zred), int(bool(cosmological)))
+
+    @property
+    def temperature_grid(self):
+        """(n3, n2, n1, 3) float32 view: current, average, intermed (temperature_module.F90:21-25)"""
+        p = self.L.orc_temperature_grid(self.h)
+        return np.ctypeslib.as_array(p, shape=(3 * self.ncell,)).reshape(self.shape + (3,))
+
+    @property
+    def phiheat(self):
+        p = self.L.orc_phiheat(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.ncell,)).reshape(self.shape)
 
     def set_dump_iteration(self, niter):
         """write_iteration_dump (evolve.F90:285-324) after pass_all_sources of iteration `niter` (0 = never)"""

@@ -59,7 +59,9 @@ def test_python_constants_match_oracle():
 
 def test_struct_layouts_match_header_sizes():
     # sizes implied by the header (no padding surprises between ctypes and the C structs)
-    assert C.sizeof(L.Config) == 14 * 4 + 18 * 8
+    assert C.sizeof(L.Config) == 14 * 4 + 25 * 8 + 2 * 4
+    cfg = L.default_config()
+    assert cfg.cosmological == 1 and cfg.k_B == 1.381e-16 and abs(cfg.gamma1 - 2.0 / 3.0) < 1e-15 and cfg.minitemp == 1.0
     assert C.sizeof(L.PhotonStats) == 12 * 8
     assert C.sizeof(L.PassReport) == 5 * 8
     assert C.sizeof(L.GlobalReport) == 8 + 2 * 8 + 12 * 8 + 8
@@ -83,10 +85,6 @@ def test_bad_config_is_rejected_before_touching_cuda():
     cfg = L.default_config()
     cfg.mesh[0], cfg.mesh[1], cfg.mesh[2] = 2048, 2048, 2048      # 2^33 cells: default-integer cell counts would overflow
     assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 101 and b"2^31" in lib.c2b_last_error(None)
-    cfg = L.default_config()
-    cfg.isothermal = 0
-    assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 102
-    assert b"isothermal" in lib.c2b_last_error(None)
     cfg = L.default_config()
     cfg.rank, cfg.nranks = 3, 2
     assert lib.c2b_create(C.byref(cfg), C.byref(h)) == 103
