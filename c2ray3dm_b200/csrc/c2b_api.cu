@@ -558,6 +558,12 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
   h->h_nbox = nullptr; h->h_loss = nullptr;
+  // the same source list again (a host that re-sends its state every step): keep the per-source trace lengths
+  // the work queue is ordered by
+  const bool same_sources = NumSrc == h->NumSrc && NumSrc > 0 && (int)h->nbox_pred.size() == NumSrc &&
+                            std::equal(srcpos, srcpos + 3 * (size_t)NumSrc, h->srcpos.begin());
+  std::vector<int> kept_pred;
+  if (same_sources) kept_pred = h->nbox_pred;
   h->NumSrc = NumSrc;
   h->S_star = S_star;
   h->work.clear();
@@ -566,6 +572,7 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
   h->nwork = (int)h->work.size();
   h->nbox_pred.assign((size_t)NumSrc, 0);
+  if (same_sources) h->nbox_pred = kept_pred;
   {
     // Z-order (Morton) key of the source cell: consecutive work items are spatial neighbours, so the traces
     // in flight at the same time share grid lines in L2

@@ -42,6 +42,14 @@ module c2ray_b200_iface
      real(c_double) :: sqrt2, sqrt3
      real(c_double) :: bh00, albpow, colh0, temph0
      real(c_double) :: abu_c
+     real(c_double) :: k_B
+     real(c_double) :: gamma1
+     real(c_double) :: minitemp
+     real(c_double) :: relative_denergy
+     real(c_double) :: tau_heat_limit
+     real(c_double) :: H0, Omega0
+     integer(c_int32_t) :: cosmological
+     integer(c_int32_t) :: reserved1
   end type c2b_config
 
   !> struct c2b_photon_stats
@@ -243,6 +251,86 @@ module c2ray_b200_iface
        real(c_double),intent(in) :: phih(*), xh_av(*), xh_intermed(*)
      end function c2b_set_iter_state
 
+     integer(c_int) function c2b_get_iter_state(handle,niter,photon_loss_all,phih,xh_av,xh_intermed) &
+          bind(C,name="c2b_get_iter_state")
+       import
+       type(c_ptr),value :: handle
+       integer(c_int32_t),intent(out) :: niter
+       real(c_double),intent(out) :: photon_loss_all
+       real(c_double),intent(out) :: phih(*), xh_av(*), xh_intermed(*)
+     end function c2b_get_iter_state
+
+     integer(c_int) function c2b_device_count() bind(C,name="c2b_device_count")
+       import
+     end function c2b_device_count
+
+     ! ---- non-isothermal path (isothermal=.false.) ---------------------------------------------------
+     integer(c_int) function c2b_set_heat_tables(handle,heat_thick,heat_thin,n) bind(C,name="c2b_set_heat_tables")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),intent(in) :: heat_thick(*), heat_thin(*)
+       integer(c_int32_t),value :: n
+     end function c2b_set_heat_tables
+
+     integer(c_int) function c2b_set_cooling_table(handle,log10_temp,log10_cool,n) bind(C,name="c2b_set_cooling_table")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),intent(in) :: log10_temp(*), log10_cool(*)
+       integer(c_int32_t),value :: n
+     end function c2b_set_cooling_table
+
+     integer(c_int) function c2b_set_redshift(handle,zred) bind(C,name="c2b_set_redshift")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),value :: zred
+     end function c2b_set_redshift
+
+     !> temperature_grid(mesh(1),mesh(2),mesh(3)) of type(temperature_states): three default reals per cell;
+     !! pass c_loc(temperature_grid) (the derived type is not interoperable by name, its storage is)
+     integer(c_int) function c2b_set_temperature_grid(handle,tg) bind(C,name="c2b_set_temperature_grid")
+       import
+       type(c_ptr),value :: handle
+       type(c_ptr),value :: tg
+     end function c2b_set_temperature_grid
+
+     integer(c_int) function c2b_get_temperature_grid(handle,tg) bind(C,name="c2b_get_temperature_grid")
+       import
+       type(c_ptr),value :: handle
+       type(c_ptr),value :: tg
+     end function c2b_get_temperature_grid
+
+     integer(c_int) function c2b_get_phiheat(handle,phiheat) bind(C,name="c2b_get_phiheat")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),intent(out) :: phiheat(*)
+     end function c2b_get_phiheat
+
+     integer(c_int) function c2b_set_iter_state_thermal(handle,phiheat,tg) bind(C,name="c2b_set_iter_state_thermal")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),intent(in) :: phiheat(*)
+       type(c_ptr),value :: tg
+     end function c2b_set_iter_state_thermal
+
   end interface
+
+contains
+
+  !> c2b_last_error as a Fortran string
+  function c2b_error_text (handle) result(text)
+    type(c_ptr),intent(in) :: handle
+    character(len=512) :: text
+    character(kind=c_char),pointer :: p(:)
+    type(c_ptr) :: cp
+    integer :: i
+    text=" "
+    cp=c2b_last_error(handle)
+    if (.not.c_associated(cp)) return
+    call c_f_pointer(cp,p,(/512/))
+    do i=1,512
+       if (p(i) == c_null_char) exit
+       text(i:i)=p(i)
+    enddo
+  end function c2b_error_text
 
 end module c2ray_b200_iface

@@ -15,7 +15,11 @@ namespace c2ray {
 
 namespace sizes { extern int mesh[3]; }                                   // sizes.f90:33
 namespace my_mpi { extern int rank, npr; }                                // mpi.F90 / no_mpi.F90
-namespace file_admin { extern std::ostream* logf; extern std::ostream* timefile; }  // file_admin.f90:20-31
+namespace file_admin {                                                    // file_admin.f90:20-31
+extern std::ostream* logf;
+extern std::ostream* timefile;
+extern std::string dump_dir;   // where iterdump1.bin / iterdump2.bin go
+}
 namespace grid { extern double dr[3], vol; }                              // grid.F90:25,29
 namespace density_module { extern std::vector<float> ndens; }            // density_module.F90:22
 namespace ionfractions_module { extern std::vector<double> xh; }         // ionfractions_module.F90:22
@@ -48,7 +52,11 @@ extern double totrec, totcollisions, dh0, total_ion, LLS_loss, grtotal_ion, grto
 namespace evolve {
 // subroutine evolve3D (time,dt,restart), evolve.F90:83.  Failures of the device library are reported the
 // way the reference reports trouble: a line in logf; `last_error()` holds the text, `ok()` is false.
+// restart: 0 = fresh step; 1, 2, 3 = start from iterdump1.bin, iterdump2.bin, iterdump.bin (evolve.F90:349-356)
 void evolve3D(double time, double dt, int restart);
+// seconds of wall clock between iteration dumps (15 minutes in the reference, evolve.F90:259); a test sets 0 to
+// get a dump after every pass_all_sources
+extern double dump_interval_seconds;
 bool ok();
 const std::string& last_error();
 int last_niter();

@@ -3,8 +3,10 @@
 // statement.
 #include "c2ray_host.hpp"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <fstream>
 #include <iomanip>
 #include <iostream>
 
@@ -14,7 +16,7 @@ namespace c2ray {
 
 namespace sizes { int mesh[3] = {0, 0, 0}; }
 namespace my_mpi { int rank = 0, npr = 1; }
-namespace file_admin { std::ostream* logf = &std::cout; std::ostream* timefile = nullptr; }
+namespace file_admin { std::ostream* logf = &std::cout; std::ostream* timefile = nullptr; std::string dump_dir = "./"; }
 namespace grid { double dr[3] = {0, 0, 0}, vol = 0; }
 namespace density_module { std::vector<float> ndens; }
 namespace ionfractions_module { std::vector<double> xh; }
@@ -38,12 +40,19 @@ double totrec = 0, totcollisions = 0, dh0 = 0, total_ion = 0, LLS_loss = 0, grto
 
 namespace evolve {
 
+double dump_interval_seconds = 15.0 * 60.0;   // evolve.F90:259
+
 namespace {
 c2b_handle* handle = nullptr;
+// what the device already holds (uploads happen only when the host changed the data)
+std::vector<int32_t> dev_srcpos;
+std::vector<double> dev_normflux;
+double dev_clumping_sig = -1.0, dev_LLS_sig = -1.0;
+int ndump = 0;
 std::string g_error;
 bool g_ok = true;
 int g_niter = 0;
-double prev_sum_xh1_int, prev_sum_xh0_int, rel_change_sum_xh1, rel_change_sum_xh0;
+double prev_sum_xh1_int = 0.0, prev_sum_xh0_int = 0.0, rel_change_sum_xh1 = 1.0, rel_change_sum_xh0 = 1.0;
 
 bool check(int rc, const char* what) {
   if (rc == 0) return true;
@@ -60,7 +69,9 @@ bool b200_init() {
   for (int d = 0; d < 3; ++d) cfg.mesh[d] = sizes::mesh[d];
   cfg.rank = my_mpi::rank;
   cfg.nranks = my_mpi::npr;
-  cfg.device = my_mpi::rank % 8;
+  // one rank per GPU: the device ordinal is the rank within the node (single node here)
+  const int ndev = c2b_device_count();
+  cfg.device = ndev > 0 ? my_mpi::rank % ndev : 0;
   cfg.type_of_clumping = c2ray_parameters::type_of_clumping;
   cfg.use_LLS = c2ray_parameters::use_LLS ? 1 : 0;
   cfg.type_of_LLS = c2ray_parameters::type_of_LLS;
@@ -81,29 +92,123 @@ bool b200_init() {
                "c2b_set_tables");
 }
 
-// the module state evolve3D reads (SURVEY 8b "hidden inputs")
+// a cheap signature of a grid the host may have replaced: size plus a strided sample
+double grid_signature(const std::vector<float>& a) {
+  double sig = (double)a.size();
+  for (size_t i = 0; i < a.size(); i += 343) sig += (double)a[i];
+  return sig;
+}
+
+// the module state evolve3D reads (SURVEY 8b "hidden inputs").  ndens, dr, vol and xh change every step;
+// sources, clumping and LLS grids only with a new slice, so they are uploaded only when they differ from what
+// the device holds.
 bool b200_upload_state() {
   using namespace c2ray_parameters;
   if (!check(c2b_set_density(handle, density_module::ndens.data()), "c2b_set_density")) return false;
   if (!check(c2b_set_geometry(handle, grid::dr, grid::vol), "c2b_set_geometry")) return false;
   if (!check(c2b_set_temperature(handle, temperature_module::temper_val), "c2b_set_temperature")) return false;
   if (type_of_clumping >= 3) {
-    if (!check(c2b_set_clumping_grid(handle, clumping_module::clumping_grid.data()), "c2b_set_clumping_grid")) return false;
+    const double sig = grid_signature(clumping_module::clumping_grid);
+    if (sig != dev_clumping_sig) {
+      if (!check(c2b_set_clumping_grid(handle, clumping_module::clumping_grid.data()), "c2b_set_clumping_grid")) return false;
+      dev_clumping_sig = sig;
+    }
   } else if (!check(c2b_set_clumping_scalar(handle, clumping_module::clumping), "c2b_set_clumping_scalar")) {
     return false;
   }
   if (use_LLS) {
     int rc = 0;
-    if (type_of_LLS == 1) rc = c2b_set_lls_scalar(handle, LLS_module::coldensh_LLS);
-    else if (type_of_LLS == 2) rc = c2b_set_lls_grid(handle, LLS_module::LLS_grid.data());
-    else rc = c2b_set_lls_rmax(handle, LLS_module::R_max_LLS);
+    if (type_of_LLS == 1) {
+      rc = c2b_set_lls_scalar(handle, LLS_module::coldensh_LLS);
+    } else if (type_of_LLS == 2) {
+      const double sig = grid_signature(LLS_module::LLS_grid);
+      if (sig != dev_LLS_sig) {
+        rc = c2b_set_lls_grid(handle, LLS_module::LLS_grid.data());
+        dev_LLS_sig = sig;
+      }
+    } else {
+      rc = c2b_set_lls_rmax(handle, LLS_module::R_max_LLS);
+    }
     if (!check(rc, "c2b_set_lls")) return false;
   }
-  if (!check(c2b_set_sources(handle, sourceprops::NumSrc, sourceprops::srcpos.data(),
-                             sourceprops::NormFlux_stellar.data(), radiation_sed_parameters::S_star),
-             "c2b_set_sources"))
-    return false;
+  if (sourceprops::srcpos != dev_srcpos || sourceprops::NormFlux_stellar != dev_normflux) {
+    if (!check(c2b_set_sources(handle, sourceprops::NumSrc, sourceprops::srcpos.data(),
+                               sourceprops::NormFlux_stellar.data(), radiation_sed_parameters::S_star),
+               "c2b_set_sources"))
+      return false;
+    dev_srcpos = sourceprops::srcpos;
+    dev_normflux = sourceprops::NormFlux_stellar;
+  }
   return check(c2b_set_xh(handle, ionfractions_module::xh.data()), "c2b_set_xh");
+}
+
+// one record of a Fortran sequential unformatted file: 4-byte length, payload, 4-byte length
+void write_record(std::ofstream& f, const void* p, size_t bytes) {
+  const uint32_t n = (uint32_t)bytes;
+  f.write(reinterpret_cast<const char*>(&n), 4);
+  f.write(reinterpret_cast<const char*>(p), (std::streamsize)bytes);
+  f.write(reinterpret_cast<const char*>(&n), 4);
+}
+bool read_record(std::ifstream& f, void* p, size_t bytes) {
+  uint32_t n0 = 0, n1 = 0;
+  f.read(reinterpret_cast<char*>(&n0), 4);
+  if (!f || n0 != bytes) return false;
+  f.read(reinterpret_cast<char*>(p), (std::streamsize)bytes);
+  f.read(reinterpret_cast<char*>(&n1), 4);
+  return (bool)f && n1 == n0;
+}
+
+// write_iteration_dump, evolve.F90:285-324: the arrays are fetched from the device at the reference's dump
+// point, between pass_all_sources and global_pass; records niter | photon_loss_all | phih_grid | xh_av | xh_intermed
+bool write_iteration_dump(int niter) {
+  const size_t n = (size_t)sizes::mesh[0] * sizes::mesh[1] * sizes::mesh[2];
+  evolve_data::phih_grid.resize(n);
+  evolve_data::xh_av.resize(n);
+  evolve_data::xh_intermed.resize(n);
+  int32_t niter_dev = 0;
+  if (!check(c2b_get_iter_state(handle, &niter_dev, &evolve_data::photon_loss_all[0], evolve_data::phih_grid.data(),
+                                evolve_data::xh_av.data(), evolve_data::xh_intermed.data()),
+             "c2b_get_iter_state"))
+    return false;
+  ndump = ndump + 1;
+  const std::string iterfile = (ndump % 2 == 0) ? "iterdump2.bin" : "iterdump1.bin";
+  std::ofstream f(file_admin::dump_dir + iterfile, std::ios::binary);
+  const int32_t nit = niter;
+  write_record(f, &nit, sizeof(nit));
+  write_record(f, evolve_data::photon_loss_all, sizeof(double));
+  write_record(f, evolve_data::phih_grid.data(), n * sizeof(double));
+  write_record(f, evolve_data::xh_av.data(), n * sizeof(double));
+  write_record(f, evolve_data::xh_intermed.data(), n * sizeof(double));
+  return (bool)f;
+}
+
+// start_from_dump, evolve.F90:328-426
+bool start_from_dump(int restart, int& niter) {
+  const bool root = my_mpi::rank == 0 && file_admin::logf;
+  const size_t n = (size_t)sizes::mesh[0] * sizes::mesh[1] * sizes::mesh[2];
+  const char* iterfile = restart == 1 ? "iterdump1.bin" : (restart == 2 ? "iterdump2.bin" : "iterdump.bin");
+  std::ifstream f(file_admin::dump_dir + iterfile, std::ios::binary);
+  evolve_data::phih_grid.resize(n);
+  evolve_data::xh_av.resize(n);
+  evolve_data::xh_intermed.resize(n);
+  int32_t nit = 0;
+  if (!f || !read_record(f, &nit, sizeof(nit)) || !read_record(f, evolve_data::photon_loss_all, sizeof(double)) ||
+      !read_record(f, evolve_data::phih_grid.data(), n * sizeof(double)) ||
+      !read_record(f, evolve_data::xh_av.data(), n * sizeof(double)) ||
+      !read_record(f, evolve_data::xh_intermed.data(), n * sizeof(double))) {
+    g_ok = false;
+    g_error = std::string("cannot read ") + file_admin::dump_dir + iterfile;
+    if (root) *file_admin::logf << "c2ray_b200 error: " << g_error << "\n";
+    return false;
+  }
+  niter = nit;
+  if (root) {
+    *file_admin::logf << "Read iteration " << niter << " from dump file\n";
+    *file_admin::logf << "photon loss counter: " << evolve_data::photon_loss_all[0] << "\n";
+  }
+  return check(c2b_set_iter_state(handle, niter, evolve_data::photon_loss_all[0], evolve_data::phih_grid.data(),
+                                  evolve_data::xh_av.data(), evolve_data::xh_intermed.data()),
+               "c2b_set_iter_state");
 }
 
 void absorb_stats(const c2b_photon_stats& s) {
@@ -135,6 +240,9 @@ int last_niter() { return g_niter; }
 void shutdown() {
   if (handle) c2b_destroy(handle);
   handle = nullptr;
+  dev_srcpos.clear();
+  dev_normflux.clear();
+  dev_clumping_sig = dev_LLS_sig = -1.0;
 }
 
 void evolve3D(double time, double dt, int restart) {
@@ -146,12 +254,15 @@ void evolve3D(double time, double dt, int restart) {
   if (!handle && !b200_init()) return;
   if (!b200_upload_state()) return;
 
+  const auto wallclock0 = std::chrono::steady_clock::now();
+  auto wallclock1 = wallclock0;
   int niter = 0;
   int conv_flag = 0;
   double sum_xh1_int = 0.0;
+  // state_before(xh) ; xh_av=xh ; xh_intermed=xh  (evolve.F90:136-147; on a restart the dump overwrites the two
+  // work arrays right below, as in the reference)
+  if (!check(c2b_begin_step(handle, &sum_xh1_int), "c2b_begin_step")) return;
   if (restart == 0) {
-    // state_before ; xh_av=xh ; xh_intermed=xh  (evolve.F90:136-147)
-    if (!check(c2b_begin_step(handle, &sum_xh1_int), "c2b_begin_step")) return;
     niter = 0;
     conv_flag = mesh[0] * mesh[1] * mesh[2];
     prev_sum_xh1_int = (double)(2.0f * (float)mesh[0] * (float)mesh[1] * (float)mesh[2]);
@@ -159,16 +270,11 @@ void evolve3D(double time, double dt, int restart) {
     rel_change_sum_xh1 = 1.0;
     rel_change_sum_xh0 = 1.0;
   } else {
-    // start_from_dump (evolve.F90:328-426): the caller has filled phih_grid, xh_av, xh_intermed,
-    // photon_loss_all from iterdump[12].bin and passes the dumped niter as `restart`
+    // Reload xh_av,xh_intermed,photon_loss,niter ; global_pass (evolve.F90:154-158); prev_sum_xh*_int keep the
+    // values they have (zero in a freshly started run)
     c2b_global_report gr;
-    if (!check(c2b_begin_step(handle, &sum_xh1_int), "c2b_begin_step")) return;
-    if (!check(c2b_set_iter_state(handle, restart, evolve_data::photon_loss_all[0], evolve_data::phih_grid.data(),
-                                  evolve_data::xh_av.data(), evolve_data::xh_intermed.data()),
-               "c2b_set_iter_state"))
-      return;
+    if (!start_from_dump(restart, niter)) return;
     if (!check(c2b_global_pass(handle, dt, &gr), "c2b_global_pass")) return;
-    niter = restart;
     conv_flag = gr.conv_flag;
     sum_xh1_int = gr.sum_xh_intermed;
   }
@@ -207,6 +313,17 @@ void evolve3D(double time, double dt, int restart) {
     evolve_source::sum_nbox_all = (int)pr.sum_nbox_all;
     if (root)
       logf << "Average number of subboxes: " << (float)evolve_source::sum_nbox_all / (float)sourceprops::NumSrc << "\n";
+
+    if (my_mpi::rank == 0) {
+      // Write iteration dump if more than 15 minutes have passed (evolve.F90:248-266)
+      const auto wallclock2 = std::chrono::steady_clock::now();
+      const double elapsed = std::chrono::duration<double>(wallclock2 - wallclock1).count();
+      if (root) logf << "Time and limit are: " << elapsed << " " << dump_interval_seconds << "\n";
+      if (elapsed > dump_interval_seconds || dump_interval_seconds <= 0.0) {
+        if (!write_iteration_dump(niter)) return;
+        wallclock1 = wallclock2;
+      }
+    }
 
     // global_pass (evolve.F90:499-573)
     c2b_global_report gr;

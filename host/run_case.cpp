@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <string>
 
 #include "c2ray_host.hpp"
 
@@ -17,7 +18,15 @@ template <class T>
 static void rd(std::ifstream& f, T* p, size_t n) { f.read(reinterpret_cast<char*>(p), sizeof(T) * n); }
 
 int main(int argc, char** argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: run_case <case.bin> <out.bin> [log.txt]\n"); return 2; }
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: run_case <case.bin> <out.bin> [log.txt [dump_dir [dump_interval_s [restart]]]]\n");
+    return 2;
+  }
+  // optional: where iterdump[12].bin go, the dump interval (0 = after every pass) and the restart flag of the
+  // first evolve3D call (1/2: start from iterdump1.bin/iterdump2.bin, evolve.F90:349-356)
+  if (argc > 4) file_admin::dump_dir = std::string(argv[4]) + "/";
+  if (argc > 5) evolve::dump_interval_seconds = std::atof(argv[5]);
+  const int restart_first = (argc > 6) ? std::atoi(argv[6]) : 0;
   std::ifstream f(argv[1], std::ios::binary);
   if (!f) { std::fprintf(stderr, "cannot open %s\n", argv[1]); return 2; }
   std::ofstream logfile;
@@ -66,7 +75,7 @@ int main(int argc, char** argv) {
     for (int d = 0; d < 3; ++d) grid::dr[d] *= zfactor;
     grid::vol *= z3;
     for (auto& v : density_module::ndens) v = (float)((double)v / z3);
-    evolve::evolve3D(sim_time, dt, 0);                       // C2Ray.F90:379
+    evolve::evolve3D(sim_time, dt, step == 0 ? restart_first : 0);   // C2Ray.F90:379 (iter_restart on the first call)
     if (!evolve::ok()) { std::fprintf(stderr, "evolve3D failed: %s\n", evolve::last_error().c_str()); return 1; }
     sim_time += dt;
     const int32_t niter = evolve::last_niter();

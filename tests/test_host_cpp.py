@@ -97,3 +97,71 @@ def test_cpp_host_history_matches_oracle(case, tmp_path):
     for line in ("Convergence tests:", "Doing all sources", "Average number of subboxes:", "Doing global",
                  "Number of non-converged points:", "Multiple sources convergence reached"):
         assert line in log      # the log lines of evolve.F90 survive the swap
+
+
+def _read_fortran_records(path, dtypes_counts):
+    """reads the records of a Fortran sequential unformatted file (4-byte length markers)"""
+    raw = open(path, "rb").read()
+    off, out = 0, []
+    for dt, cnt in dtypes_counts:
+        n0 = struct.unpack_from("<I", raw, off)[0]
+        assert n0 == np.dtype(dt).itemsize * cnt
+        out.append(np.frombuffer(raw, dtype=dt, count=cnt, offset=off + 4))
+        assert struct.unpack_from("<I", raw, off + 4 + n0)[0] == n0
+        off += 8 + n0
+    assert off == len(raw)
+    return out
+
+
+@pytest.mark.gpu
+def test_cpp_host_dump_and_restart_match_oracle(tmp_path):
+    """write_iteration_dump / start_from_dump of the host (evolve.F90:285-426): a run that dumps after every
+    pass_all_sources leaves iterdump1.bin / iterdump2.bin with the reference's record layout (niter |
+    photon_loss_all | phih_grid | xh_av | xh_intermed); the records match the oracle's dump of the same iteration,
+    and a second process restarted from the file (restart = 1 or 2) ends exactly where the uninterrupted run did"""
+    from oracle import oracle as O
+    tables = O.rad_ini()[:2]
+    p = make_problem(N=24, nsrc=5, seed=41, state="random", use_LLS=True)
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    n = 24 ** 3
+    cfile, lfile = tmp_path / "case.bin", tmp_path / "log.txt"
+    _write_case(str(cfile), p, tables, 1, 1.0)
+    # uninterrupted run, dumping after every pass
+    r = subprocess.run([DRV, str(cfile), str(tmp_path / "full.bin"), str(lfile), str(tmp_path), "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw = open(tmp_path / "full.bin", "rb").read()
+    niter_full = struct.unpack_from("<i", raw, 0)[0]
+    xh_full = np.frombuffer(raw, dtype=np.float64, count=n, offset=52)
+    assert niter_full >= 3
+    layout = [(np.int32, 1), (np.float64, 1), (np.float64, n), (np.float64, n), (np.float64, n)]
+    d1 = _read_fortran_records(tmp_path / "iterdump1.bin", layout)
+    d2 = _read_fortran_records(tmp_path / "iterdump2.bin", layout)
+    # the two files hold the last odd-numbered and the last even-numbered dump
+    its = sorted([int(d1[0][0]), int(d2[0][0])])
+    assert its == [niter_full - 1, niter_full]
+    # the oracle's dump of the same iteration
+    for d in (d1, d2):
+        k = int(d[0][0])
+        o = setup_oracle(p, tables=tables)
+        o.set_dump_iteration(k)
+        ro = o.evolve3D(DT)
+        assert ro.niter == niter_full
+        nit, pl, ph, xav, xint = o.get_dump()
+        assert nit == k and float(d[1][0]) == pytest.approx(pl, rel=1e-6)
+        nz = ph.reshape(-1) != 0
+        assert np.max(np.abs(d[2][nz] - ph.reshape(-1)[nz]) / ph.reshape(-1)[nz]) <= 1e-6
+        np.testing.assert_allclose(d[3], xav.reshape(-1), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(d[4], xint.reshape(-1), rtol=0, atol=1e-6)
+    # restart a fresh process from the older of the two dumps (the other one is the final iteration)
+    which = 1 if int(d1[0][0]) == niter_full - 1 else 2
+    r = subprocess.run([DRV, str(cfile), str(tmp_path / "rest.bin"), str(tmp_path / "log2.txt"), str(tmp_path),
+                        "1e9", str(which)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    raw2 = open(tmp_path / "rest.bin", "rb").read()
+    assert struct.unpack_from("<i", raw2, 0)[0] == niter_full
+    xh_rest = np.frombuffer(raw2, dtype=np.float64, count=n, offset=52)
+    np.testing.assert_allclose(xh_rest, xh_full, rtol=0, atol=1e-12)
+    log2 = open(tmp_path / "log2.txt").read()
+    assert "Read iteration %d from dump file" % (niter_full - 1) in log2
+    assert "Multiple sources convergence reached" in log2
