@@ -169,7 +169,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_sample(w, mesh, nsample, threads, keep=False):
+def cpu_sample(w, mesh, nsample, threads, keep=False, in_source=False):
     """times the C restatement (oracle/) on a bounded sample: one pass over every k-th source + one
     per-cell pass, on `threads` host threads (sources dealt to threads, private rate grids summed: the
     reference's MPI picture).  Returns (updates/s, description, seconds, updates[, source selection, rate grid])."""
@@ -185,6 +185,7 @@ def cpu_sample(w, mesh, nsample, threads, keep=False):
     o.set_sources(w["srcpos"][sel], w["normflux"][sel], 1e48)
     o.set_xh(w["xh"])
     o.set_threads(threads)
+    o.set_omp_in_source(in_source)
     o.xh_av[...] = w["xh"]
     o.xh_intermed[...] = w["xh"]
     o.state_before()
@@ -196,8 +197,11 @@ def cpu_sample(w, mesh, nsample, threads, keep=False):
     o.global_pass(0.5e6 * YEAR, r.photon_loss_all)
     t2 = time.perf_counter()
     desc = ("%d of %d sources (every %dth, file order) of the %d^3 workload: 1 pass_all_sources (%.2fs) + "
-            "1 global_pass (%.2fs), C restatement, %d threads, mode: source-parallel (one source per thread, private "
-            "rate grids summed: do_grid_static + MPI_ALLREDUCE)" % (len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads))
+            "1 global_pass (%.2fs), C restatement, %d threads, mode: %s" % (
+                len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads,
+                "omp-in-source (all threads inside one source: 6 axes / 12 planes / 8 octants, evolve_source.F90:141-186)"
+                if in_source else "source-parallel (one source per thread, private rate grids summed: do_grid_static + "
+                                  "MPI_ALLREDUCE)"))
     if keep:
         return r.updates / (t1 - t0), desc, t2 - t0, r.updates, sel, phih
     return r.updates / (t1 - t0), desc, t2 - t0, r.updates
@@ -429,6 +433,9 @@ def run_ours(args):
             nsample = min(len(w["normflux"]), int(nsample * 15 / max(s, 1e-3)))
             v, desc, s, u, sel, ph_cpu = cpu_sample(w, mesh, nsample, cores, keep=True)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        # the reference's other parallel mode: OpenMP inside each source, at most 12-way
+        v2, desc2, s2, u2 = cpu_sample(w, mesh, max(8, len(sel) // 6), cores, in_source=True)
+        line["cpu_baseline"]["omp_in_source"] = {"value": v2, "unit": UNIT, "cores": cores, "sample": desc2}
         # parity of the timed workload: the same sampled sources, one pass from the S1 snapshot, GPU vs CPU
         e.set_sources(w["srcpos"][sel], w["normflux"][sel])
         e.set_xh(xh_pin.numpy())

@@ -263,7 +263,8 @@ template <int kFpg, int kTg, bool kGlobal, bool kClip, bool kR1, int kLls, bool 
 __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, const Face* __restrict__ faces, int gtid,
                                             const double2* __restrict__ s_thick, const double2* __restrict__ s_logtab,
                                             const double2* __restrict__ s_heat, const LogC& L, int r, const double* __restrict__ prev,
-                                            double* __restrict__ cur, int fstride, int nseg, double& loss, int& min_hi) {
+                                            double* __restrict__ cur, int fstride, int nseg, int* next_item,
+                                            double& loss, int& min_hi) {
   if (kGlobal) {
     __builtin_assume(__isGlobal(prev));
     __builtin_assume(__isGlobal(cur));
@@ -280,7 +281,16 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
   const double inv_r = fast_rcp(rd);
   const double r2d = rd * rd;
   const bool loss_shell = (r == S.reach);   // non-clipped shells: every cell of the shell is on the subbox boundary, or none
-  for (int it = gtid; it < nitem; it += kTg) {
+  // The work items of the shell are handed out 32 at a time from a counter in shared memory: a warp whose cells
+  // are cheap (stopped behind the 2e19 column: no rates) simply takes more of them, so the warps of the group
+  // reach the barrier of the shell together.
+  for (;;) {
+    int it = 0;
+    if ((threadIdx.x & 31) == 0) it = atomicAdd(next_item, 32);
+    it = __shfl_sync(0xffffffffu, it, 0);
+    if (it >= nitem) break;
+    it += (int)(threadIdx.x & 31);
+    if (it < nitem) do {   // (a `continue` below leaves this item)
     // work item = (segment of b, face, column a), a fastest so that a warp spans adjacent columns
     const int seg = (nseg == 1) ? 0 : (int)(((float)it + 0.5f) * inv_ncol);
     const int c = it - seg * ncol;
@@ -454,6 +464,7 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
       t2 = t4;
       bd += 1.0;
     }
+    } while (0);
   }
 }
 
@@ -475,6 +486,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
   constexpr int kTg = (kCluster == 1) ? kTgCta : kT;    // threads per group
   constexpr int kGroups = kNf / kFpg;
   __shared__ int s_gmin[kGroups][3];                // dead-face rule: smallest high word per group, rotating by shell
+  __shared__ int s_next[kGroups][2];                // next work item of the shell, alternating by shell parity
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int g = tid / kTg;                          // face group of this thread
@@ -509,6 +521,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
   for (;;) {
     // ---- next source (device-side do_grid_master: one ticket per work group) ---------------------
     __syncthreads();
+    if (tid < kGroups * 2) (&s_next[0][0])[tid] = 0;
     if (crank == 0 && tid == 0) s_work = (int)atomicAdd(P.ticket, 1u);
     int w;
     if (kCluster > 1) {
@@ -597,6 +610,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       // a face walk its shells on their own and the work group meets again only for the loss of the pass.
       for (int r = r_done + 1; r <= rmax; ++r) {
         int min_hi = 0x7fffffff;   // high word of the smallest optical depth this thread writes to plane r
+        if (gtid == 0) s_next[g][(r + 1) & 1] = 0;   // the counter of shell r+1 (nobody uses it before the barrier below)
         if (!face_dead) {
           const int P1 = r + 1;
           const int nseg = (kCluster == 1) ? P.nseg_cta[r] : P.nseg_cl[r];   // host-tuned split of the columns along b
@@ -607,9 +621,9 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
           if (cur_sm) {
             double* cur = (r & 1) ? sbuf1 : sbuf0;
             const double* prev = (r & 1) ? sbuf0 : sbuf1;
-            if (r == 1) trace_shell<kFpg, kTg, false, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
-            else if (r < S.rsafe) trace_shell<kFpg, kTg, false, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
-            else trace_shell<kFpg, kTg, false, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, loss, min_hi);
+            if (r == 1) trace_shell<kFpg, kTg, false, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[g][r & 1], loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, false, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[g][r & 1], loss, min_hi);
+            else trace_shell<kFpg, kTg, false, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[g][r & 1], loss, min_hi);
           } else {
             double* cur = (r & 1) ? gbuf1 : gbuf0;
             double* gprev = (r & 1) ? gbuf0 : gbuf1;
@@ -620,9 +634,9 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
                 for (int i = gtid; i < 4 * r * r; i += kTg) gprev[f * gstride + i] = sprev[f * sstride + i];
               group_sync<kTg>(g);
             }
-            if (r == 1) trace_shell<kFpg, kTg, true, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
-            else if (r < S.rsafe) trace_shell<kFpg, kTg, true, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
-            else trace_shell<kFpg, kTg, true, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, loss, min_hi);
+            if (r == 1) trace_shell<kFpg, kTg, true, false, true, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, &s_next[g][r & 1], loss, min_hi);
+            else if (r < S.rsafe) trace_shell<kFpg, kTg, true, false, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, &s_next[g][r & 1], loss, min_hi);
+            else trace_shell<kFpg, kTg, true, true, false, kLls, kDebug, kHeat>(P, S, faces, gtid, s_thick, s_logtab, s_heat, L, r, gprev, cur, gstride, nseg, &s_next[g][r & 1], loss, min_hi);
           }
         }
         // plane r complete before plane r+1 reads it.  Dead-face rule: once every optical depth of the planes of a
@@ -795,6 +809,11 @@ int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info) {
 // threads that walk a group of `nf` faces, i.e. nf*(r+1) columns of four cells per row.
 static void build_nseg_table(int max_radius, int nf, int threads, std::vector<int>& tab) {
   tab.assign((size_t)max_radius + 2, 1);
+  if (const char* env = getenv("C2B_RT_SEGLEN")) {   // development knob: fixed target segment length
+    const int target = std::max(1, atoi(env));
+    for (int r = 1; r <= max_radius; ++r) tab[r] = std::min(64, (r + 1 + target - 1) / target);
+    return;
+  }
   for (int r = 1; r <= max_radius; ++r) {
     const int P1 = r + 1, ncol = nf * P1;
     long best = -1;

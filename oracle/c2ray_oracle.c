@@ -310,6 +310,7 @@ struct orc_state {
   double loss_fraction;
   int walk_order;
   int rank, npr, nthreads;
+  int omp_in_source; /* 1: the threads share one source (evolve_source.F90:141-186), 0: one source per thread */
   /* photonstatistics module variables */
   double h0_before, h1_before, h0_after, h1_after, totrec, totcollisions, dh0, total_ion;
   double LLS_loss, photon_loss, grtotal_ion, grtotal_src;
@@ -415,6 +416,10 @@ void orc_set_loss_fraction(orc_state *s, double lf) { s->loss_fraction = lf; }
 void orc_set_walk_order(orc_state *s, int order) { s->walk_order = order; }
 void orc_set_rank(orc_state *s, int rank, int npr) { s->rank = rank; s->npr = npr; }
 void orc_set_threads(orc_state *s, int n) { s->nthreads = n < 1 ? 1 : n; }
+/* how orc_set_threads(n > 1) is used by pass_all_sources: 0 = one source per thread with private rate grids (the MPI
+ * picture, do_grid_static + MPI_ALLREDUCE), 1 = all threads inside one source (the OpenMP build,
+ * evolve_source.F90:141-186: 6 axes, 12 planes, 8 octants) */
+void orc_set_omp_in_source(orc_state *s, int on) { s->omp_in_source = on ? 1 : 0; }
 
 /* ---- non-isothermal inputs ------------------------------------------------------------------ */
 /* isothermal=.false. (c2ray_parameters.f90:28): allocates phiheat_grid (evolve_data.F90:77) and
@@ -827,7 +832,37 @@ static void do_source(const orc_state *s, double *coldensh_out, double *phih_gri
       w.last_r[d] = r < lastpos_r[d] ? r : lastpos_r[d];
       w.last_l[d] = l > lastpos_l[d] ? l : lastpos_l[d];
     }
-    if (s->walk_order == 1) { /* OpenMP branch :141-186 executed by one thread */
+    if (s->omp_in_source && s->nthreads > 1) {
+      /* OpenMP branch :141-186 executed by nthreads threads: the source cell, then the 6 axes, the 12 planes and
+       * the 8 octants, each group shared between the threads with a barrier after it.  The sweeps of a group
+       * touch disjoint cells; every sweep adds its boundary loss to a private counter
+       * (photon_loss_src_thread(tn)), summed afterwards in sweep order. */
+      if (nbox == 1) { int rtpos[3] = {src[0], src[1], src[2]}; evolve0D(&w, rtpos, ns); }
+      static const int A[6][3] = {{1,0,0},{-1,0,0},{0,1,0},{0,-1,0},{0,0,1},{0,0,-1}};
+      static const int P[12][3] = {{1,1,0},{1,-1,0},{-1,1,0},{-1,-1,0},{1,0,1},{-1,0,1},{-1,0,-1},{1,0,-1},
+                                   {0,1,1},{0,-1,1},{0,1,-1},{0,-1,-1}};
+      static const int Q[8][3] = {{1,1,1},{-1,1,1},{1,-1,1},{-1,-1,1},{1,1,-1},{-1,1,-1},{1,-1,-1},{-1,-1,-1}};
+      const int (*groups[3])[3] = {A, P, Q};
+      const int count[3] = {6, 12, 8};
+      double part_loss[12];
+      int64_t part_upd[12];
+      for (int g = 0; g < 3; ++g) {
+#pragma omp parallel for num_threads(s->nthreads) schedule(dynamic, 1)
+        for (int n = 0; n < count[g]; ++n) {
+          walk_ctx wl = w;
+          wl.photon_loss_src_thread = 0.0;
+          wl.updates = 0;
+          sweep_signed(&wl, ns, groups[g][n]);
+          part_loss[n] = wl.photon_loss_src_thread;
+          part_upd[n] = wl.updates;
+        }
+        for (int n = 0; n < count[g]; ++n) {
+          w.photon_loss_src_thread = w.photon_loss_src_thread + part_loss[n];
+          w.updates += part_upd[n];
+        }
+      }
+      photon_loss_src = photon_loss_src + w.photon_loss_src_thread;
+    } else if (s->walk_order == 1) { /* OpenMP branch :141-186 executed by one thread */
       if (nbox == 1) { int rtpos[3] = {src[0], src[1], src[2]}; evolve0D(&w, rtpos, ns); }
       /* axes 1..6: +i,-i,+j,-j,+k,-k */
       for (int d = 0; d < 3; ++d) for (int sg = 1; sg >= -1; sg -= 2) {
@@ -875,7 +910,7 @@ void orc_pass_all_sources(orc_state *s, orc_pass_report *rep) {
   int64_t sum_nbox = 0, updates = 0;
   double photon_loss = 0.0;
   const int mine = (s->NumSrc - s->rank + s->npr - 1) / s->npr; /* sources of this rank */
-  if (s->nthreads <= 1 || mine <= 1) {
+  if (s->nthreads <= 1 || mine <= 1 || s->omp_in_source) {
     for (int ns1 = 1 + s->rank; ns1 <= s->NumSrc; ns1 += s->npr) {
       orc_source_report r;
       do_source(s, s->coldensh_out, s->phih_grid, s->phiheat_grid, ns1, &r);

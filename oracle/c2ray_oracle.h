@@ -68,6 +68,9 @@ void orc_set_walk_order(orc_state *s, int order);
 void orc_set_rank(orc_state *s, int rank, int npr);
 /* number of OpenMP threads used by orc_pass_all_sources in source-parallel CPU-baseline mode. */
 void orc_set_threads(orc_state *s, int nthreads);
+/* 0 (default): one source per thread, private rate grids summed (do_grid_static + MPI_ALLREDUCE);
+ * 1: all threads inside one source as in the OpenMP build (evolve_source.F90:141-186) */
+void orc_set_omp_in_source(orc_state *s, int on);
 
 /* ---- non-isothermal path (isothermal=.false.; thermal.f90, cooling.f90, heat_lookuptable) ---------- */
 void orc_rad_ini_heat(double *thick, double *thin, double *heat_thick, double *heat_thin);

@@ -106,6 +106,7 @@ def lib():
         L.orc_set_walk_order.argtypes = [vp, C.c_int]
         L.orc_set_rank.argtypes = [vp, C.c_int, C.c_int]
         L.orc_set_threads.argtypes = [vp, C.c_int]
+        L.orc_set_omp_in_source.argtypes = [vp, C.c_int]
         for f in ("orc_xh", "orc_xh_av", "orc_xh_intermed", "orc_phih", "orc_coldensh_out"):
             getattr(L, f).restype = dp
             getattr(L, f).argtypes = [vp]
@@ -258,6 +259,10 @@ class Oracle:
         self.L.orc_set_threads(self.h, int(n))
 
     # -- grids --------------------------------------------------------------------------------
+    def set_omp_in_source(self, on):
+        """threads inside one source (the OpenMP build, evolve_source.F90:141-186) instead of one source per thread"""
+        self.L.orc_set_omp_in_source(self.h, int(bool(on)))
+
     def _grid(self, fn):
         p = getattr(self.L, fn)(self.h)
         return np.ctypeslib.as_array(p, shape=(self.ncell,)).reshape(self.shape)

@@ -376,3 +376,23 @@ def test_upstream_cells_outside_previous_shell_have_zero_weight():
                     cp[q[2], q[1], q[0]] = 1e300
                 checked += 1
     assert checked > 1500
+
+
+def test_omp_in_source_mode_is_exact():
+    """the reference's OpenMP build (evolve_source.F90:141-186: all threads inside one source, 6 axes / 12 planes /
+    8 octants with a barrier after each group) gives bit-identical rates: the sweeps of a group touch disjoint cells"""
+    p = make_problem(20, nsrc=3, seed=31, state="random", use_LLS=True)
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    a = setup_oracle(p)
+    a.xh_av[...] = p["xh"]
+    a.set_rates_to_zero()
+    ra = a.pass_all_sources()
+    b = setup_oracle(p)
+    b.set_threads(4)
+    b.set_omp_in_source(True)
+    b.xh_av[...] = p["xh"]
+    b.set_rates_to_zero()
+    rb = b.pass_all_sources()
+    assert (ra.updates, ra.sum_nbox_all) == (rb.updates, rb.sum_nbox_all)
+    assert np.array_equal(a.phih, b.phih)
+    assert rb.photon_loss_all == pytest.approx(ra.photon_loss_all, rel=1e-12)
