@@ -81,7 +81,12 @@ struct c2b_handle {
   bool taucell_dirty = true;   // xh_av / ndens / dr changed since tau_cell was last formed
   RtLaunchInfo rt;             // shared-memory plane capacities and resident grid sizes
   int* d_work2 = nullptr;      // work list of the cluster kernel
-  int *d_nseg_cta = nullptr, *d_nseg_cl = nullptr;
+  int* d_work3 = nullptr;      // work list of the per-warp kernel (traces that ended after one subbox last time)
+  int* d_ovf = nullptr;        // sources the per-warp kernel hands over to the single-CTA kernel
+  int warp_min_sources = 0;    // the per-warp kernel is used when at least this many sources qualify
+  unsigned int* h_ovf = nullptr;   // pinned: number of handed-over sources of the last pass
+  long long route_counts[4] = {0, 0, 0, 0};
+  int *d_nseg_cta = nullptr, *d_nseg_cl = nullptr, *d_nseg_w = nullptr;
   std::vector<int> nbox_pred;  // per source: nbox of the previous trace (routing + longest-first order)
   int cluster_min_nbox = 3;    // sources predicted to need >= this many subboxes may go to the cluster kernel
   int cluster_max_sources = 0; // ... but only while there are too few of them to fill the GPU one CTA each
@@ -285,7 +290,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMemsetAsync(h->d_phih, 0, n * sizeof(double), h->stream)) != cudaSuccess) return bail("memset", e);
   if ((e = cudaMalloc(&h->d_thick, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_thin, kTableLen * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&h->d_ticket, 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
+  // [0] single-CTA kernel, [1] cluster kernel, [2] per-warp kernel, [3] number of handed-over sources
+  if ((e = cudaMalloc(&h->d_ticket, 4 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_taucell, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell", e);
   if ((e = cudaMalloc(&h->d_taucell_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc tau_cell_t", e);
   if ((e = cudaMalloc(&h->d_phih_t, n * sizeof(double))) != cudaSuccess) return bail("cudaMalloc phih_t", e);
@@ -327,14 +333,20 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
     smax = std::max(smax, std::max(h->lim[d][0], h->lim[d][1]));
   }
   h->plane_stride = smax + 1;
-  if (raytrace_configure(smax, !cfg->isothermal, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
+  int smin = smax;
+  for (int d = 0; d < 3; ++d) smin = std::min(smin, std::min(h->lim[d][0], h->lim[d][1]));
+  if (raytrace_configure(smax, !cfg->isothermal, cfg->subboxsize, smin, &h->rt)) return bail("raytrace_configure", cudaGetLastError());
+  h->warp_min_sources = 2 * h->rt.grid_warp;
+  if (const char* env = getenv("C2B_WARP_MIN_SOURCES")) h->warp_min_sources = atoi(env);
   h->rt_grid = h->rt.grid_max;
   h->cluster_max_sources = 4 * h->rt.clusters;
   if (const char* env = getenv("C2B_CLUSTER_MIN_NBOX")) h->cluster_min_nbox = atoi(env);
   if (const char* env = getenv("C2B_CLUSTER_MAX_SOURCES")) h->cluster_max_sources = atoi(env);
   {
-    std::vector<int> t_cta, t_cl;
-    raytrace_nseg_tables(smax, t_cta, t_cl);
+    std::vector<int> t_cta, t_cl, t_w;
+    raytrace_nseg_tables(smax, t_cta, t_cl, t_w);
+    if ((e = cudaMalloc(&h->d_nseg_w, t_w.size() * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemcpy(h->d_nseg_w, t_w.data(), t_w.size() * sizeof(int), cudaMemcpyHostToDevice);
     if ((e = cudaMalloc(&h->d_nseg_cta, t_cta.size() * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_nseg_cl, t_cl.size() * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemcpy(h->d_nseg_cta, t_cta.data(), t_cta.size() * sizeof(int), cudaMemcpyHostToDevice);
@@ -351,6 +363,8 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMalloc(&h->d_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMallocHost(&h->h_stats, kNumStat * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&h->h_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&h->h_ovf, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMallocHost", e);
+  *h->h_ovf = 0u;
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("sync", e);
   *out = h;
   return 0;
@@ -363,8 +377,8 @@ void c2b_destroy(c2b_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->d_ndens); cudaFree(h->d_xh); cudaFree(h->d_xh_av); cudaFree(h->d_xh_intermed);
   cudaFree(h->d_phih); cudaFree(h->d_clump); cudaFree(h->d_lls); cudaFree(h->d_f32tmp);
-  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_taucell_t); cudaFree(h->d_phih_t); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
-  cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
+  cudaFree(h->d_thick); cudaFree(h->d_thin); cudaFree(h->d_taucell); cudaFree(h->d_taucell_t); cudaFree(h->d_phih_t); cudaFree(h->d_thick2); cudaFree(h->d_logtab); cudaFree(h->d_nseg_cta); cudaFree(h->d_nseg_cl); cudaFree(h->d_nseg_w); cudaFree(h->d_srcpos); cudaFree(h->d_normflux);
+  cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_work3); cudaFree(h->d_ovf); cudaFree(h->d_nbox); cudaFree(h->d_loss); cudaFree(h->d_ticket);
   cudaFree(h->d_xh_saved);
   cudaFree(h->d_phiheat); cudaFree(h->d_phiheat_t); cudaFree(h->d_heat_thick); cudaFree(h->d_heat_thin); cudaFree(h->d_heat2);
   cudaFree(h->d_cie_cool); cudaFree(h->d_Tcur); cudaFree(h->d_Tavg); cudaFree(h->d_Tint); cudaFree(h->d_Taos);
@@ -373,6 +387,7 @@ void c2b_destroy(c2b_handle* h) {
   if (h->h_loss) cudaFreeHost(h->h_loss);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_small) cudaFreeHost(h->h_small);
+  if (h->h_ovf) cudaFreeHost(h->h_ovf);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : h->ev_step)
@@ -552,8 +567,8 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
       if (srcpos[3 * s + d] < 1 || srcpos[3 * s + d] > h->cfg.mesh[d])
         return fail(h, "c2b_set_sources: source position outside the mesh (positions are 1-based)");
   if (bind_device(h)) return 1;
-  cudaFree(h->d_srcpos); cudaFree(h->d_normflux); cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_nbox); cudaFree(h->d_loss);
-  h->d_work2 = nullptr;
+  cudaFree(h->d_srcpos); cudaFree(h->d_normflux); cudaFree(h->d_work); cudaFree(h->d_work2); cudaFree(h->d_work3); cudaFree(h->d_ovf); cudaFree(h->d_nbox); cudaFree(h->d_loss);
+  h->d_work2 = nullptr; h->d_work3 = nullptr; h->d_ovf = nullptr;
   h->d_srcpos = nullptr; h->d_normflux = nullptr; h->d_work = nullptr; h->d_nbox = nullptr; h->d_loss = nullptr;
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
@@ -604,6 +619,8 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   CU(h, cudaMalloc(&h->d_normflux, ns * sizeof(double)));
   CU(h, cudaMalloc(&h->d_work, std::max<size_t>(1, h->work.size()) * sizeof(int)));
   CU(h, cudaMalloc(&h->d_work2, std::max<size_t>(1, h->work.size()) * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_work3, std::max<size_t>(1, h->work.size()) * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_ovf, std::max<size_t>(1, h->work.size()) * sizeof(int)));
   CU(h, cudaMalloc(&h->d_nbox, ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_loss, ns * sizeof(double)));
   CU(h, cudaMallocHost(&h->h_nbox, ns * sizeof(int)));
@@ -806,9 +823,10 @@ static void absorb_after(c2b_handle* h, double dt) {
   h->total_ion = h->totrec + h->dh0;
 }
 
-// traces the sources of d_work (one CTA each) and of d_work_cl (one cluster of 8 CTAs each)
+// traces the sources of d_work (one CTA each), of d_work_cl (one cluster of 6 CTAs each) and of d_work_w (one warp
+// each for the first subbox; those that need more are handed over to the single-CTA kernel on the device)
 static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int* d_work_cl, int nwork_cl,
-                         double* coldens_dbg, float* ms) {
+                         const int* d_work_w, int nwork_w, double* coldens_dbg, float* ms) {
   const c2b_config& c = h->cfg;
   RtParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -843,6 +861,10 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.work = d_work;
   rp.nseg_cta = h->d_nseg_cta;
   rp.nseg_cl = h->d_nseg_cl;
+  rp.nseg_w = h->d_nseg_w;
+  rp.warp_plane_doubles = h->rt.warp_plane_doubles;
+  rp.ovf = h->d_ovf;
+  rp.ovf_count = nullptr;
   rp.nwork = nwork;
   rp.ticket = h->d_ticket;
   rp.scratch = h->d_scratch;
@@ -884,7 +906,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   }
   CU(h, cudaMemsetAsync(h->d_phih_t, 0, h->ncell * sizeof(double), h->stream));
   if (h->d_phiheat_t) CU(h, cudaMemsetAsync(h->d_phiheat_t, 0, h->ncell * sizeof(double), h->stream));
-  CU(h, cudaMemsetAsync(h->d_ticket, 0, 2 * sizeof(unsigned int), h->stream));
+  CU(h, cudaMemsetAsync(h->d_ticket, 0, 4 * sizeof(unsigned int), h->stream));
   CU(h, cudaEventRecord(h->ev[0], h->stream));
   if (nwork_cl > 0) {  // long traces first: one cluster per source, planes in shared memory
     RtParams rc = rp;
@@ -899,13 +921,24 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     }
     h->launches += 1;
   }
-  if (nwork > 0) {
-    const int grid = std::min(h->rt.grid_cta, nwork);
+  if (nwork_w > 0) {   // first subbox of the short traces, one warp per source
+    RtParams rw = rp;
+    rw.work = d_work_w;
+    rw.nwork = nwork_w;
+    rw.ticket = h->d_ticket + 2;
+    rw.ovf_count = h->d_ticket + 3;
+    launch_raytrace_warp(rw, std::min(h->rt.grid_warp, (nwork_w + h->rt.warp_warps - 1) / h->rt.warp_warps), h->rt.warp_warps, h->stream);
+    h->launches += 1;
+    CU(h, cudaGetLastError());
+    rp.ovf_count = h->d_ticket + 3;   // the single-CTA kernel also takes what the per-warp kernel handed over
+  }
+  if (nwork > 0 || nwork_w > 0) {
+    const int grid = std::min(h->rt.grid_cta, nwork + nwork_w);
     launch_raytrace(rp, grid, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
   }
-  if (nwork > 0 || nwork_cl > 0) {
+  if (nwork > 0 || nwork_cl > 0 || nwork_w > 0) {
     launch_add_from_yfast(h->d_phih, h->d_phih_t, c.mesh, h->stream);
     h->launches += 1;
     if (h->d_phiheat) {
@@ -976,7 +1009,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     // source already fills the GPU and has less synchronisation, so the cluster kernel is used only
     // while the long traces are few.  Sources never traced before (prediction 0) count as long when the
     // whole list is short.
-    std::vector<int> small, large;
+    std::vector<int> small, large, tiny;
     const bool few = (int)h->work.size() <= h->cluster_max_sources;
     const bool zorder = !(getenv("C2B_NO_ZORDER") && atoi(getenv("C2B_NO_ZORDER")));
     for (int w : (zorder ? h->work_morton : h->work)) {
@@ -997,16 +1030,33 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       v.clear();
       for (int b = mx; b >= 0; --b) v.insert(v.end(), bucket[(size_t)b].begin(), bucket[(size_t)b].end());
     };
+    // traces that ended after one subbox last time: one warp per source, if there are enough of them to fill the GPU
+    if (h->rt.warp_warps > 0 && !(getenv("C2B_NO_WARP_KERNEL") && atoi(getenv("C2B_NO_WARP_KERNEL")))) {
+      int n1 = 0;
+      for (int w : small) n1 += h->nbox_pred[w] == 1;
+      if (n1 >= h->warp_min_sources) {
+        std::vector<int> rest;
+        for (int w : small) (h->nbox_pred[w] == 1 ? tiny : rest).push_back(w);
+        small.swap(rest);
+      }
+    }
     by_nbox_desc(large);
     by_nbox_desc(small);
+    if (!tiny.empty())
+      CU(h, cudaMemcpyAsync(h->d_work3, tiny.data(), tiny.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!small.empty())
       CU(h, cudaMemcpyAsync(h->d_work, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!large.empty())
       CU(h, cudaMemcpyAsync(h->d_work2, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), nullptr, &ms_rt)) return rc;
+    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), h->d_work3, (int)tiny.size(), nullptr, &ms_rt)) return rc;
     CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_ovf, h->d_ticket + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    h->route_counts[0] += (long long)small.size();
+    h->route_counts[1] += (long long)large.size();
+    h->route_counts[2] += (long long)tiny.size();
+    h->route_counts[3] += (long long)*h->h_ovf;
     // photon_loss(1)=photon_loss(1)+photon_loss_src ; sum_nbox=sum_nbox+nbox, in source order
     for (int w : h->work) {
       h->nbox_pred[w] = h->h_nbox[w];
@@ -1341,7 +1391,7 @@ int c2b_trace_source_debug(c2b_handle* h, int32_t ns, double* coldensh_out, doub
   // C2B_DEBUG_CLUSTER=1 sends the diagnostic trace through the cluster kernel
   const char* envc = getenv("C2B_DEBUG_CLUSTER");
   const bool use_cl = envc && atoi(envc) != 0;
-  int rc = use_cl ? trace_sources(h, nullptr, 0, d_one, 1, d_dbg, nullptr) : trace_sources(h, d_one, 1, nullptr, 0, d_dbg, nullptr);
+  int rc = use_cl ? trace_sources(h, nullptr, 0, d_one, 1, nullptr, 0, d_dbg, nullptr) : trace_sources(h, d_one, 1, nullptr, 0, nullptr, 0, d_dbg, nullptr);
   if (!rc && coldensh_out) rc = download(h, coldensh_out, d_dbg, h->ncell * 8, "coldensh_out");
   if (!rc && phih) rc = download(h, phih, h->d_phih, h->ncell * 8, "phih");
   int nb = 0;
@@ -1353,6 +1403,13 @@ int c2b_trace_source_debug(c2b_handle* h, int32_t ns, double* coldensh_out, doub
   cudaFree(d_dbg);
   cudaFree(d_one);
   return rc;
+}
+
+int c2b_get_route_counts(c2b_handle* h, int64_t counts[4]) {
+  C2B_CHECK_H(h);
+  if (!counts) return fail(h, "c2b_get_route_counts: null argument");
+  for (int i = 0; i < 4; ++i) counts[i] = (int64_t)h->route_counts[i];
+  return 0;
 }
 
 int c2b_measure_dfma_rate(c2b_handle* h, double* dfma_per_s) {

@@ -46,6 +46,10 @@ struct RtParams {
   const int* work;          // source indices (0-based) this rank traces, in order
   const int* nseg_cta;      // per shell radius: b-segments per column (single-CTA kernel / cluster kernel)
   const int* nseg_cl;
+  const int* nseg_w;        // same for the per-warp kernel (32 threads walk the six faces)
+  int warp_plane_doubles;   // capacity of one shared-memory plane buffer of the per-warp kernel
+  int* ovf;                 // sources the per-warp kernel hands over to the single-CTA kernel after their first subbox
+  unsigned int* ovf_count;  // ... and how many (written by the per-warp kernel; read by the single-CTA kernel when non-null)
   int nwork;
   unsigned int* ticket;     // dynamic work counter (plays do_grid_master, master_slave.F90:124-231)
   double* scratch;          // per-work-group global plane storage: [grid][2][6 faces][face_doubles]
@@ -74,11 +78,16 @@ struct RtLaunchInfo {
   int clusters;    // resident clusters of the cluster kernel
   int cluster_size;
   int grid_max;    // CTAs the scratch must be sized for
+  int warp_warps;  // warps (= concurrent sources) per CTA of the per-warp kernel; 0: not usable for this mesh / subboxsize
+  int warp_plane_doubles;
+  int grid_warp;   // CTAs of the per-warp kernel (one per SM)
 };
 // sets the kernels' shared-memory attributes and queries the resident grid sizes
-int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info);
+// min_lim = the smallest half-box limit (evolve_source.F90:100-102): the per-warp kernel needs subboxsize < min_lim
+int raytrace_configure(int max_radius, bool heat_tables, int subboxsize, int min_lim, RtLaunchInfo* info);
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream);
-void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl);
+void launch_raytrace_warp(const RtParams& p, int grid, int warps, cudaStream_t stream);
+void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl, std::vector<int>& warp);
 void launch_taucell(const float* ndens, const double* xh_av, double* tau_cell, size_t n, double sigma_dr0,
                     double eps, cudaStream_t stream);
 void launch_pair_table(const double* tab, double2* out, cudaStream_t stream);

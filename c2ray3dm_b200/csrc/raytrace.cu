@@ -250,6 +250,8 @@ struct SrcCtx {
   double normflux;
   int reach;      // subboxsize*nbox of this pass
   int rsafe;      // shells r < rsafe are not clipped by the periodic half box on any side
+  bool emit;      // this pass adds rates and counts the boundary loss (false: a dark source, or a pass that only
+                  // rebuilds the planes of shells the per-warp kernel has already emitted)
 };
 
 // One shell of one source: the cells with Chebyshev distance r of the faces this CTA owns.
@@ -314,7 +316,7 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
       if (a == F.lrA) losscol |= 0x5u;
       if (a == F.llA) losscol |= 0xAu;
     }
-    if (!(S.normflux > 0.0)) colmask = 0u;            // a dark source is never traced (evolve_source.F90:119-131)
+    if (!S.emit) colmask = 0u;                        // a dark source is never traced (evolve_source.F90:119-131)
     const int nrow = bend - b0 + 1;
     if (nrow <= 0) continue;
     const int own_hi = (F.p == 0) ? r : r - 1;        // b == r belongs to the z-principal face
@@ -468,6 +470,35 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
   }
 }
 
+// per-face constants of one subbox pass.  face f: p = f mod 3 (0: z, 1: y, 2: x principal), positive side first.
+// axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z) on the y-fastest twins (index (x*n2+z)*n1+y)
+__device__ __forceinline__ Face make_face(const RtParams& P, int f, int src0, int src1, int src2, int lr0, int ll0,
+                                          int lr1, int ll1, int lr2, int ll2) {
+  const int p = (f >= 3) ? f - 3 : f, sp = (f >= 3) ? -1 : 1;
+  const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
+  Face F;
+  F.p = p; F.sp = sp; F.pad_ = 0;
+  F.srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
+  F.srcA = (p == 2) ? src1 : src0;
+  F.srcB = (p == 0) ? src1 : src2;
+  F.nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
+  F.nA = (p == 2) ? n1 : n0;
+  F.nB = (p == 0) ? n1 : n2;
+  F.strP = (p == 0) ? (unsigned)n0 * (unsigned)n1 : (p == 1 ? (unsigned)n0 : (unsigned)n1 * (unsigned)n2);
+  F.strB = (p == 0) ? (unsigned)n0 : (p == 1 ? (unsigned)n0 * (unsigned)n1 : (unsigned)n1);
+  const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
+  F.limP = (sp > 0) ? lrP : llP;
+  F.lrA = (p == 2) ? lr1 : lr0; F.llA = (p == 2) ? ll1 : ll0;
+  F.lrB = (p == 0) ? lr1 : lr2; F.llB = (p == 0) ? ll1 : ll2;
+  F.dP2 = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
+  F.dA2 = (p == 2) ? P.dr2[1] : P.dr2[0];
+  F.dB2 = (p == 0) ? P.dr2[1] : P.dr2[2];
+  F.tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
+  F.phih = (p == 2) ? P.phih_t : P.phih;
+  F.heat = (p == 2) ? P.phiheat_t : P.phiheat;
+  return F;
+}
+
 // One CTA (kCluster == 1, all six faces) or one cluster of 6 CTAs (one face each) per source.
 template <int kCluster, int kLls, bool kDebug, bool kHeat>
 __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
@@ -531,8 +562,13 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       __syncthreads();
       w = s_work;
     }
-    if (w >= P.nwork) break;
-    const int ns = P.work[w];  // 0-based source index
+    // the work list, then (single-CTA kernel only) the sources the per-warp kernel handed over after their first
+    // subbox: their pass 1 is repeated without rates (`silent`), only to rebuild the planes of shell `subboxsize`
+    const int nwork_all = P.nwork + ((kCluster == 1 && P.ovf_count) ? (int)*P.ovf_count : 0);
+    if (w >= nwork_all) break;
+    const bool handed_over = w >= P.nwork;
+    const int ns = handed_over ? P.ovf[w - P.nwork] : P.work[w];  // 0-based source index
+    const int silent = handed_over ? 1 : 0;                       // passes nbox <= silent emit nothing
     const int src0 = P.srcpos[3 * ns] - 1, src1 = P.srcpos[3 * ns + 1] - 1, src2 = P.srcpos[3 * ns + 2] - 1;
     S.normflux = P.normflux[ns];
     const double total_source_flux = S.normflux * P.S_star;  // evolve_source.F90:119
@@ -547,38 +583,12 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       nbox += 1;
       const int reach = P.subboxsize * nbox;  // :135-136
       S.reach = reach;
+      S.emit = S.normflux > 0.0 && nbox > silent;
       lr0 = min(reach, P.lim[0][1]); ll0 = min(reach, P.lim[0][0]);
       lr1 = min(reach, P.lim[1][1]); ll1 = min(reach, P.lim[1][0]);
       lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
       const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
-      if (tid < kNf) {
-        // face f: p = f mod 3 (0: z, 1: y, 2: x principal), positive side first.
-        // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z) on the y-fastest twins (index (x*n2+z)*n1+y)
-        const int f = (int)crank * kNf + tid;
-        const int p = (f >= 3) ? f - 3 : f, sp = (f >= 3) ? -1 : 1;
-        const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
-        Face F;
-        F.p = p; F.sp = sp; F.pad_ = 0;
-        F.srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
-        F.srcA = (p == 2) ? src1 : src0;
-        F.srcB = (p == 0) ? src1 : src2;
-        F.nP = (p == 0) ? n2 : (p == 1 ? n1 : n0);
-        F.nA = (p == 2) ? n1 : n0;
-        F.nB = (p == 0) ? n1 : n2;
-        F.strP = (p == 0) ? (unsigned)n0 * (unsigned)n1 : (p == 1 ? (unsigned)n0 : (unsigned)n1 * (unsigned)n2);
-        F.strB = (p == 0) ? (unsigned)n0 : (p == 1 ? (unsigned)n0 * (unsigned)n1 : (unsigned)n1);
-        const int lrP = (p == 0) ? lr2 : (p == 1 ? lr1 : lr0), llP = (p == 0) ? ll2 : (p == 1 ? ll1 : ll0);
-        F.limP = (sp > 0) ? lrP : llP;
-        F.lrA = (p == 2) ? lr1 : lr0; F.llA = (p == 2) ? ll1 : ll0;
-        F.lrB = (p == 0) ? lr1 : lr2; F.llB = (p == 0) ? ll1 : ll2;
-        F.dP2 = (p == 0) ? P.dr2[2] : (p == 1 ? P.dr2[1] : P.dr2[0]);
-        F.dA2 = (p == 2) ? P.dr2[1] : P.dr2[0];
-        F.dB2 = (p == 0) ? P.dr2[1] : P.dr2[2];
-        F.tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
-        F.phih = (p == 2) ? P.phih_t : P.phih;
-        F.heat = (p == 2) ? P.phiheat_t : P.phiheat;
-        s_face[tid] = F;
-      }
+      if (tid < kNf) s_face[tid] = make_face(P, (int)crank * kNf + tid, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2);
       double loss = 0.0;
       if (r_done < 0) {
         // shell 0 = the source cell (evolve_point.F90:151-160): coldensh_in=0, path=dr/2, vol_ph=cell volume.
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
           s_planes[(size_t)(2 * (tid >> 2)) * (cap + kPadFront) + kPadFront + (tid & 3)] = tau_out;   // plane 0 of face tid/4, quadrant tid%4
           if (crank == 0 && tid == 0) {
             if (kDebug) P.coldens_dbg[cell] = tau_out * P.inv_sigma;
-            if (S.normflux > 0.0) {
+            if (S.emit) {
               double phi_all, phi_out, heat_all = 0.0;
               photo_rates<kHeat>(0.0, tau_out, S.normflux, s_thick, s_logtab, s_heat, P, L, phi_all, phi_out, heat_all);
               // rate = phi_all/(vol_cell*nHI), nHI = tau_cell/(sigma*dr0)
@@ -665,7 +675,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       if (kCluster == 1) {
         double t = 0.0;
         for (int i = 0; i < kT / 32; ++i) t += s_red[i];   // same order in every thread
-        photon_loss_src = t;
+        if (nbox > silent) photon_loss_src = t;            // (a silent pass keeps the loop going: its loss was > the cut-off)
       } else {
         if (tid == 0) {
           double t = 0.0;
@@ -688,6 +698,106 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
     if (kCluster > 1) cluster.sync();     // every peer has read s_work before rank 0 fetches the next ticket
   }
   if (kCluster > 1) cluster.sync();  // nobody leaves while a peer may still read rank 0's shared memory
+}
+
+// The first subbox of many short traces: ONE WARP per source, kWarpMax warps per CTA, one CTA per SM.
+// Early in reionization every trace ends after one or two subboxes (a few hundred to a few thousand cells); a whole CTA
+// per source then spends its time in barriers and in the latency chain ticket -> source -> first loads, with two
+// sources in flight per SM.  Here a warp walks shells 0..subboxsize of its source alone (planes in its own slice of
+// shared memory, __syncwarp between shells), so an SM has up to 10-12 independent traces in flight.  A source whose
+// loss after this first subbox still exceeds the cut-off (evolve_source.F90:128-131) is handed over: the single-CTA
+// kernel, launched next, repeats its pass 1 without rates and carries on from pass 2.  The host routes a source here
+// only when its previous trace ended after one subbox, and only if subboxsize < every half-box limit (no clipping).
+constexpr int kWarpMax = 12;
+
+template <int kLls, bool kHeat>
+__global__ void __launch_bounds__(32 * kWarpMax, 1) raytrace_warp_kernel(RtParams P) {
+  extern __shared__ double2 smem2[];
+  double2* s_thick = smem2;
+  double2* s_logtab = smem2 + kTableLen;
+  double2* s_heat = smem2 + kTableLen + 128;
+  double* s_planes = reinterpret_cast<double*>(smem2 + kTableLen + 128 + (kHeat ? kTableLen : 0));
+  __shared__ Face s_face[kWarpMax][kFaces];
+  __shared__ int s_next[kWarpMax];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
+  const int cap = P.warp_plane_doubles;
+  for (int i = tid; i < kTableLen; i += nthreads) s_thick[i] = P.thick2[i];
+  for (int i = tid; i < 128; i += nthreads) s_logtab[i] = P.logtab[i];
+  if (kHeat)
+    for (int i = tid; i < kTableLen; i += nthreads) s_heat[i] = P.heat2[i];
+  const int per_warp = 2 * kFaces * (cap + kPadFront);
+  for (int i = tid; i < (nthreads >> 5) * per_warp; i += nthreads) s_planes[i] = 0.0;
+  __syncthreads();
+  double* wbase = s_planes + (size_t)wid * per_warp;
+  double* sbuf0 = wbase + kPadFront;
+  double* sbuf1 = sbuf0 + cap + kPadFront;
+  const int sstride = 2 * (cap + kPadFront);
+  LogC L;
+  L.c0 = P.logc[0]; L.c1 = P.logc[1]; L.c2 = P.logc[2]; L.c3 = P.logc[3]; L.c4 = P.logc[4]; L.B = P.logB;
+  SrcCtx S;
+  S.rsafe = min(min(min(P.lim[0][0], P.lim[0][1]), min(P.lim[1][0], P.lim[1][1])), min(P.lim[2][0], P.lim[2][1]));
+  const int reach = P.subboxsize;   // nbox = 1; the host guarantees reach < rsafe
+  S.reach = reach;
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = (int)atomicAdd(P.ticket, 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= P.nwork) break;
+    const int ns = P.work[w];
+    const int src0 = P.srcpos[3 * ns] - 1, src1 = P.srcpos[3 * ns + 1] - 1, src2 = P.srcpos[3 * ns + 2] - 1;
+    S.normflux = P.normflux[ns];
+    S.emit = S.normflux > 0.0;
+    const double total_source_flux = S.normflux * P.S_star;   // evolve_source.F90:119
+    if (!(total_source_flux > P.loss_fraction * total_source_flux)) {   // the do while of :128 is never entered
+      if (lane == 0) {
+        P.nbox_out[ns] = 0;
+        P.loss_out[ns] = total_source_flux;
+      }
+      continue;
+    }
+    __syncwarp();   // the lanes are done with the previous source's faces and planes
+    if (lane < kFaces) s_face[wid][lane] = make_face(P, lane, src0, src1, src2, reach, reach, reach, reach, reach, reach);
+    if (lane < 4 * kFaces) {
+      // shell 0 = the source cell (evolve_point.F90:151-160), plane 0 of every quadrant
+      const unsigned cell = ((unsigned)src2 * (unsigned)P.n[1] + (unsigned)src1) * (unsigned)P.n[0] + (unsigned)src0;
+      const double tau_cell = P.tau_cell[cell];
+      const double tau_out = 0.5 * tau_cell;
+      wbase[(size_t)(2 * (lane >> 2)) * (cap + kPadFront) + kPadFront + (lane & 3)] = tau_out;
+      if (lane == 0) {
+        double phi_all, phi_out, heat_all = 0.0;
+        photo_rates<kHeat>(0.0, tau_out, S.normflux, s_thick, s_logtab, s_heat, P, L, phi_all, phi_out, heat_all);
+        const double photo_cell = phi_all * fast_rcp(P.vol_cell * tau_cell * P.inv_sigma_dr0);
+        if (photo_cell != 0.0) atomicAdd(&P.phih[cell], photo_cell);
+        if (kHeat) {
+          const double heat_cell = heat_all * fast_rcp(P.vol_cell);
+          if (heat_cell != 0.0) atomicAdd(&P.phiheat[cell], heat_cell);
+        }
+      }
+    }
+    double loss = 0.0;
+    int min_hi = 0x7fffffff;
+    for (int r = 1; r <= reach; ++r) {
+      if (lane == 0) s_next[wid] = 0;
+      __syncwarp();   // plane r-1, the faces and the work counter are visible to the warp
+      double* cur = (r & 1) ? sbuf1 : sbuf0;
+      const double* prev = (r & 1) ? sbuf0 : sbuf1;
+      const int nseg = P.nseg_w[r];
+      if (r == 1) trace_shell<kFaces, 32, false, false, true, kLls, false, kHeat>(P, S, s_face[wid], lane, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[wid], loss, min_hi);
+      else trace_shell<kFaces, 32, false, false, false, kLls, false, kHeat>(P, S, s_face[wid], lane, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[wid], loss, min_hi);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) {
+      // do while (photon_loss_src > loss_fraction*total_source_flux ...), evolve_source.F90:128-131 (the subbox is
+      // inside the half box on every side, so only the loss decides)
+      if (loss > P.loss_fraction * total_source_flux) {
+        P.ovf[atomicAdd(P.ovf_count, 1u)] = ns;   // hand over: the single-CTA kernel carries on from pass 2
+      } else {
+        P.nbox_out[ns] = 1;
+        P.loss_out[ns] = loss;
+      }
+    }
+  }
 }
 
 // tau_cell = sigma*dr(1) * max(1-max(xh_av,eps),eps) * ndens  (evolve_point.F90:137-145, doric.f90:141-155)
@@ -763,7 +873,22 @@ static void cluster_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, i
   cfg->numAttrs = 1;
 }
 
-int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info) {
+static RtKernel pick_warp_kernel(int lls, bool heat) {
+  if (heat) {
+    switch (lls) {
+      case 2: return raytrace_warp_kernel<2, true>;
+      case 3: return raytrace_warp_kernel<3, true>;
+      default: return raytrace_warp_kernel<1, true>;
+    }
+  }
+  switch (lls) {
+    case 2: return raytrace_warp_kernel<2, false>;
+    case 3: return raytrace_warp_kernel<3, false>;
+    default: return raytrace_warp_kernel<1, false>;
+  }
+}
+
+int raytrace_configure(int max_radius, bool heat_tables, int subboxsize, int min_lim, RtLaunchInfo* info) {
   int dev = 0, max_optin = 0, sm_total = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -802,6 +927,31 @@ int raytrace_configure(int max_radius, bool heat_tables, RtLaunchInfo* info) {
   info->cluster_size = kClusterSize;
   // scratch slots: one per resident CTA of the single-CTA kernel plus one per resident cluster
   info->grid_max = info->grid_cta + info->clusters;
+  // per-warp kernel: shells 0..subboxsize of one source per warp, planes of every warp in shared memory
+  info->warp_warps = 0;
+  info->warp_plane_doubles = 0;
+  info->grid_warp = sms;
+  if (subboxsize >= 1 && subboxsize < min_lim) {
+    const int P1 = subboxsize + 1;
+    const int cap_w = (4 * P1 * P1 + 4 * P1 + 8 + 3) & ~3;
+    const size_t per_warp = (size_t)2 * kFaces * (cap_w + kPadFront) * sizeof(double);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, pick_warp_kernel(1, heat_tables)) != cudaSuccess) return (int)cudaGetLastError();
+    const long room = (long)max_optin - (long)fa.sharedSizeBytes - (long)fixed - 256;
+    int nw = room > 0 ? (int)std::min<long>(kWarpMax, room / (long)per_warp) : 0;
+    if (const char* env = getenv("C2B_WARP_WARPS")) nw = std::min(nw, atoi(env));
+    if (nw >= 4) {
+      for (int lls = 1; lls < 4; ++lls)
+        for (int heat = 0; heat < 2; ++heat) {
+          const size_t fx = (size_t)(kTableLen + 128 + (heat ? kTableLen : 0)) * sizeof(double2);
+          cudaError_t e2 = cudaFuncSetAttribute(pick_warp_kernel(lls, heat != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)std::min<size_t>(max_optin - fa.sharedSizeBytes, fx + kWarpMax * per_warp));
+          if (e2 != cudaSuccess) return (int)e2;
+        }
+      info->warp_warps = nw;
+      info->warp_plane_doubles = cap_w;
+    }
+  }
   return 0;
 }
 
@@ -827,9 +977,10 @@ static void build_nseg_table(int max_radius, int nf, int threads, std::vector<in
   }
 }
 
-void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl) {
+void raytrace_nseg_tables(int max_radius, std::vector<int>& cta, std::vector<int>& cl, std::vector<int>& warp) {
   build_nseg_table(max_radius, kFpgCta, kTgCta, cta);   // single-CTA kernel: groups of kFpgCta faces
   build_nseg_table(max_radius, 1, kT, cl);              // cluster kernel: the whole CTA walks one face
+  build_nseg_table(max_radius, kFaces, 32, warp);       // per-warp kernel: one warp walks the six faces
 }
 
 static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
@@ -837,6 +988,13 @@ static int lls_mode(const RtParams& p) { return p.use_lls ? p.type_lls : 0; }
 void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
   const bool heat = p.phiheat != nullptr && p.coldens_dbg == nullptr;   // the diagnostic kernels carry no heating rates
   pick_kernel<1>(lls_mode(p), p.coldens_dbg != nullptr, heat)<<<grid, kT, rt_smem_bytes(p.smem_plane_doubles, kFaces, heat), stream>>>(p);
+}
+
+void launch_raytrace_warp(const RtParams& p, int grid, int warps, cudaStream_t stream) {
+  const bool heat = p.phiheat != nullptr;
+  const size_t smem = (size_t)(kTableLen + 128 + (heat ? kTableLen : 0)) * sizeof(double2) +
+                      (size_t)warps * 2 * kFaces * (p.warp_plane_doubles + kPadFront) * sizeof(double);
+  pick_warp_kernel(lls_mode(p), heat)<<<grid, 32 * warps, smem, stream>>>(p);
 }
 
 int launch_raytrace_cluster(const RtParams& p, int nclusters, cudaStream_t stream) {

@@ -295,6 +295,12 @@ class Evolve:
         self._ck(self.L.c2b_measure_dfma_rate(self.h, C.byref(r)), "c2b_measure_dfma_rate")
         return r.value
 
+    def route_counts(self):
+        """sources dealt so far to (one CTA, one cluster, one warp for the first subbox, handed over by the warp shape)"""
+        a = (C.c_int64 * 4)()
+        self._ck(self.L.c2b_get_route_counts(self.h, a), "c2b_get_route_counts")
+        return tuple(int(x) for x in a)
+
     def synchronize(self):
         self._ck(self.L.c2b_synchronize(self.h), "c2b_synchronize")
 

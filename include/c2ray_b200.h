@@ -212,6 +212,11 @@ int c2b_trace_source_debug(c2b_handle *h, int32_t ns, double *coldensh_out, doub
 /* measured peak rate of a dependent-free DFMA stream on this device, in FP64 instructions/s
  * (roofline denominator for the FP64-issue bound) */
 int c2b_measure_dfma_rate(c2b_handle *h, double *dfma_per_s);
+/* how this handle's sources were dealt to the three ray-trace work-group shapes since c2b_create (diagnostic;
+ * the reference has one shape, do_source on one thread, evolve_source.F90:58): counts[0] one CTA per source,
+ * [1] one cluster of 6 CTAs per source, [2] one warp per source for the first subbox, [3] of those, handed over to
+ * the one-CTA shape because their loss still exceeded loss_fraction (evolve_source.F90:128-131) */
+int c2b_get_route_counts(c2b_handle *h, int64_t counts[4]);
 
 #ifdef __cplusplus
 }

@@ -20,11 +20,17 @@ X_ATOL = 1e-6
 DT = 1e6 * 3.15576e7
 
 
-@pytest.fixture(params=["auto", "cta", "cluster"], autouse=True)
+@pytest.fixture(params=["auto", "cta", "cluster", "warp"], autouse=True)
 def routing(request, monkeypatch):
-    """every test runs with the default routing of sources to the two ray-trace kernels, with the
-    one-CTA-per-source kernel only, and with the cluster-of-6 kernel only"""
-    if request.param == "cta":
+    """every test runs with the default routing of sources to the ray-trace kernels, with the
+    one-CTA-per-source kernel only, with the cluster-of-6 kernel only, and with the one-warp-per-source kernel
+    taking every source whose previous trace ended after one subbox (the rest: one CTA per source)"""
+    monkeypatch.delenv("C2B_WARP_MIN_SOURCES", raising=False)
+    if request.param == "warp":
+        monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
+        monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
+        monkeypatch.setenv("C2B_WARP_MIN_SOURCES", "1")
+    elif request.param == "cta":
         monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
         monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
     elif request.param == "cluster":
@@ -521,4 +527,36 @@ def test_non_cubic_cells(gpu_tables):
     np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
     _rates_close(e.phih_grid, o.phih)
     assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
+    e.close()
+
+
+@pytest.mark.parametrize("lls,clump", [(1, "scalar"), (2, "grid"), (3, "scalar")], ids=["lls1", "lls_grid", "lls_rmax"])
+def test_warp_per_source_kernel_and_hand_over(lls, clump, gpu_tables, monkeypatch, routing):
+    """early reionization: many sources whose traces end after one subbox go to the one-warp-per-source kernel; the
+    bright ones outgrow the first subbox and are handed over to the one-CTA kernel on the device.  Three steps
+    against the oracle; the route counters prove both paths ran."""
+    if routing != "warp":
+        pytest.skip("runs once, with the warp routing")
+    rng = np.random.default_rng(77)
+    N, nsrc = 40, 120
+    p = make_problem(N, nsrc=nsrc, seed=31, state="neutral", use_LLS=True, type_of_LLS=lls, clumping=clump, flux=2e6)
+    p["normflux"][::7] *= 3000.0       # a few bright sources leave the first subbox within these steps
+    p["normflux"][5] = 0.0             # a dark source is never traced (evolve_source.F90:128)
+    o = setup_oracle(p, tables=gpu_tables)
+    e = setup_gpu(p, tables=gpu_tables)
+    for step in range(3):
+        ro = o.evolve3D(DT)
+        rg = e.evolve3D(step * DT, DT)
+        assert (rg.niter, rg.converged) == (ro.niter, ro.converged)
+        assert list(rg.sum_nbox_all[1:rg.niter + 1]) == list(ro.sum_nbox_all[1:ro.niter + 1])
+        assert list(rg.conv_flag[1:rg.niter + 1]) == list(ro.conv_flag[1:ro.niter + 1])
+        assert rg.total_updates == ro.total_updates
+        np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+        _rates_close(e.phih_grid, o.phih)
+        assert rg.final_stats.photcons == pytest.approx(ro.final_stats.photcons, rel=1e-6)
+        assert rg.final_stats.total_photon_loss == pytest.approx(ro.final_stats.total_photon_loss, rel=1e-6)
+    cta, cluster, warp, handed = e.route_counts()
+    assert warp > 0 and handed > 0 and cluster == 0, (cta, cluster, warp, handed)
+    nb = e.source_nbox()
+    assert nb[5] == 0 and nb.max() >= 2
     e.close()
