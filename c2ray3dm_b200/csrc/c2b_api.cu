@@ -59,7 +59,7 @@ struct c2b_handle {
   c2b_config cfg;
   size_t ncell = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_step[2] = {nullptr, nullptr};   // brackets of c2b_evolve3d
   std::string error;
   // grids
@@ -825,8 +825,11 @@ static void absorb_after(c2b_handle* h, double dt) {
 
 // traces the sources of d_work (one CTA each), of d_work_cl (one cluster of 6 CTAs each) and of d_work_w (one warp
 // each for the first subbox; those that need more are handed over to the single-CTA kernel on the device)
+// novf > 0: follow-up call after a pass in which only the per-warp kernel ran and handed `novf` sources over (they are
+// in d_ovf, their number in d_ticket[3]): the single-CTA kernel traces just those.
+// The launches are bracketed by the events ev[e0], ev[e0+1]; the caller reads the time after its own synchronisation.
 static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int* d_work_cl, int nwork_cl,
-                         const int* d_work_w, int nwork_w, double* coldens_dbg, float* ms) {
+                         const int* d_work_w, int nwork_w, int novf, double* coldens_dbg, int e0) {
   const c2b_config& c = h->cfg;
   RtParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -862,7 +865,8 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   rp.nseg_cta = h->d_nseg_cta;
   rp.nseg_cl = h->d_nseg_cl;
   rp.nseg_w = h->d_nseg_w;
-  rp.warp_plane_doubles = h->rt.warp_plane_doubles;
+  rp.warp_plane_doubles[0] = h->rt.warp_plane_doubles[0];
+  rp.warp_plane_doubles[1] = h->rt.warp_plane_doubles[1];
   rp.ovf = h->d_ovf;
   rp.ovf_count = nullptr;
   rp.nwork = nwork;
@@ -899,15 +903,21 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     h->taucell_dirty = false;
     h->taucell_t_dirty = true;
   }
-  if (h->taucell_t_dirty) {
+  // the single-CTA and the cluster kernel work on the y-fastest twins for their x-principal faces; the per-warp
+  // kernel does not, so a pass it handles alone needs neither the transposes nor the twin of the rate grid
+  const bool run_cta = nwork > 0 || novf > 0;
+  const bool need_twins = run_cta || nwork_cl > 0;
+  if (need_twins && h->taucell_t_dirty) {
     launch_to_yfast(h->d_taucell, h->d_taucell_t, c.mesh, h->stream);
     h->launches += 1;
     h->taucell_t_dirty = false;
   }
-  CU(h, cudaMemsetAsync(h->d_phih_t, 0, h->ncell * sizeof(double), h->stream));
-  if (h->d_phiheat_t) CU(h, cudaMemsetAsync(h->d_phiheat_t, 0, h->ncell * sizeof(double), h->stream));
-  CU(h, cudaMemsetAsync(h->d_ticket, 0, 4 * sizeof(unsigned int), h->stream));
-  CU(h, cudaEventRecord(h->ev[0], h->stream));
+  if (need_twins) {
+    CU(h, cudaMemsetAsync(h->d_phih_t, 0, h->ncell * sizeof(double), h->stream));
+    if (h->d_phiheat_t) CU(h, cudaMemsetAsync(h->d_phiheat_t, 0, h->ncell * sizeof(double), h->stream));
+  }
+  CU(h, cudaMemsetAsync(h->d_ticket, 0, (novf > 0 ? 3 : 4) * sizeof(unsigned int), h->stream));
+  CU(h, cudaEventRecord(h->ev[e0], h->stream));
   if (nwork_cl > 0) {  // long traces first: one cluster per source, planes in shared memory
     RtParams rc = rp;
     rc.work = d_work_cl;
@@ -921,7 +931,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     }
     h->launches += 1;
   }
-  if (nwork_w > 0) {   // first subbox of the short traces, one warp per source
+  if (nwork_w > 0 && novf == 0) {   // first subbox of the short traces, one warp per source
     RtParams rw = rp;
     rw.work = d_work_w;
     rw.nwork = nwork_w;
@@ -930,15 +940,16 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     launch_raytrace_warp(rw, std::min(h->rt.grid_warp, (nwork_w + h->rt.warp_warps - 1) / h->rt.warp_warps), h->rt.warp_warps, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
-    rp.ovf_count = h->d_ticket + 3;   // the single-CTA kernel also takes what the per-warp kernel handed over
   }
-  if (nwork > 0 || nwork_w > 0) {
-    const int grid = std::min(h->rt.grid_cta, nwork + nwork_w);
+  if (run_cta) {
+    // the single-CTA kernel also takes what the per-warp kernel handed over (in this call or, novf > 0, in the previous one)
+    if (nwork_w > 0 || novf > 0) rp.ovf_count = h->d_ticket + 3;
+    const int grid = std::min(h->rt.grid_cta, nwork + (novf > 0 ? novf : nwork_w));
     launch_raytrace(rp, grid, h->stream);
     h->launches += 1;
     CU(h, cudaGetLastError());
   }
-  if (nwork > 0 || nwork_cl > 0 || nwork_w > 0) {
+  if (need_twins) {
     launch_add_from_yfast(h->d_phih, h->d_phih_t, c.mesh, h->stream);
     h->launches += 1;
     if (h->d_phiheat) {
@@ -947,11 +958,7 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
     }
     CU(h, cudaGetLastError());
   }
-  CU(h, cudaEventRecord(h->ev[1], h->stream));
-  if (ms) {
-    CU(h, cudaEventSynchronize(h->ev[1]));
-    CU(h, cudaEventElapsedTime(ms, h->ev[0], h->ev[1]));
-  }
+  CU(h, cudaEventRecord(h->ev[e0 + 1], h->stream));
   return 0;
 }
 
@@ -1048,11 +1055,23 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       CU(h, cudaMemcpyAsync(h->d_work, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!large.empty())
       CU(h, cudaMemcpyAsync(h->d_work2, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), h->d_work3, (int)tiny.size(), nullptr, &ms_rt)) return rc;
+    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), h->d_work3, (int)tiny.size(), 0, nullptr, 0)) return rc;
     CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_ovf, h->d_ticket + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventElapsedTime(&ms_rt, h->ev[0], h->ev[1]));
+    if (small.empty() && !tiny.empty() && *h->h_ovf > 0u) {
+      // only the per-warp kernel ran and some of its sources need more than one subbox: the single-CTA kernel
+      // carries on with those (when the single-CTA kernel runs in the same pass it takes them there and then)
+      if (int rc = trace_sources(h, nullptr, 0, nullptr, 0, nullptr, 0, (int)*h->h_ovf, nullptr, 4)) return rc;
+      CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      float ms2 = 0.f;
+      CU(h, cudaEventElapsedTime(&ms2, h->ev[4], h->ev[5]));
+      ms_rt += ms2;
+    }
     h->route_counts[0] += (long long)small.size();
     h->route_counts[1] += (long long)large.size();
     h->route_counts[2] += (long long)tiny.size();
@@ -1391,7 +1410,7 @@ int c2b_trace_source_debug(c2b_handle* h, int32_t ns, double* coldensh_out, doub
   // C2B_DEBUG_CLUSTER=1 sends the diagnostic trace through the cluster kernel
   const char* envc = getenv("C2B_DEBUG_CLUSTER");
   const bool use_cl = envc && atoi(envc) != 0;
-  int rc = use_cl ? trace_sources(h, nullptr, 0, d_one, 1, nullptr, 0, d_dbg, nullptr) : trace_sources(h, d_one, 1, nullptr, 0, nullptr, 0, d_dbg, nullptr);
+  int rc = use_cl ? trace_sources(h, nullptr, 0, d_one, 1, nullptr, 0, 0, d_dbg, 0) : trace_sources(h, d_one, 1, nullptr, 0, nullptr, 0, 0, d_dbg, 0);
   if (!rc && coldensh_out) rc = download(h, coldensh_out, d_dbg, h->ncell * 8, "coldensh_out");
   if (!rc && phih) rc = download(h, phih, h->d_phih, h->ncell * 8, "phih");
   int nb = 0;

@@ -47,7 +47,7 @@ struct RtParams {
   const int* nseg_cta;      // per shell radius: b-segments per column (single-CTA kernel / cluster kernel)
   const int* nseg_cl;
   const int* nseg_w;        // same for the per-warp kernel (32 threads walk the six faces)
-  int warp_plane_doubles;   // capacity of one shared-memory plane buffer of the per-warp kernel
+  int warp_plane_doubles[2];   // capacities of the two shared-memory plane buffers (even / odd shells) of a face in the per-warp kernel
   int* ovf;                 // sources the per-warp kernel hands over to the single-CTA kernel after their first subbox
   unsigned int* ovf_count;  // ... and how many (written by the per-warp kernel; read by the single-CTA kernel when non-null)
   int nwork;
@@ -79,7 +79,7 @@ struct RtLaunchInfo {
   int cluster_size;
   int grid_max;    // CTAs the scratch must be sized for
   int warp_warps;  // warps (= concurrent sources) per CTA of the per-warp kernel; 0: not usable for this mesh / subboxsize
-  int warp_plane_doubles;
+  int warp_plane_doubles[2];
   int grid_warp;   // CTAs of the per-warp kernel (one per SM)
 };
 // sets the kernels' shared-memory attributes and queries the resident grid sizes

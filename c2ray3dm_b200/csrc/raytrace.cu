@@ -91,10 +91,12 @@ struct Face {
   int nP, nA, nB;             // mesh extents along them
   int sp;                     // sign of the principal offset
   int p;                      // 0: z, 1: y, 2: x principal (the branch order of cinterp)
-  unsigned strP, strB;        // element strides of the principal and the b axis (the a axis is contiguous)
+  unsigned strP, strB;        // element strides of the principal and the b axis
   int limP;                   // extent of this pass's subbox along sp*P
   int lrA, llA, lrB, llB;     // ... along +a, -a, +b, -b
-  int pad_;
+  unsigned strA;              // stride of the a axis: 1 (contiguous) except for the x-principal faces of the per-warp
+                              // kernel, which work on the x-fastest grids directly
+  int lay;                    // 2: this face addresses the y-fastest twins, 0: the x-fastest grids
   double dP2, dA2, dB2;       // dr^2 per axis (dist2 of evolve_point.F90:170-174)
   const double* tau;          // opacity grid (x-fastest, or the y-fastest twin for p == 2)
   double* phih;               // rate grid, same layout
@@ -322,8 +324,8 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
     const int own_hi = (F.p == 0) ? r : r - 1;        // b == r belongs to the z-principal face
     // addresses: cell = posP*strP + posA + posB*strB
     const unsigned rowP = (unsigned)wrap(F.srcP + F.sp * r, F.nP) * F.strP;
-    const unsigned baseAp = rowP + (unsigned)wrap(F.srcA + a, F.nA);
-    const unsigned baseAm = rowP + (unsigned)wrap(F.srcA - a, F.nA);
+    const unsigned baseAp = rowP + (unsigned)wrap(F.srcA + a, F.nA) * F.strA;
+    const unsigned baseAm = rowP + (unsigned)wrap(F.srcA - a, F.nA) * F.strA;
     const int nB = F.nB;
     const unsigned strB = F.strB;
     int posBp = wrap(F.srcB + b0, nB), posBm = wrap(F.srcB - b0, nB);
@@ -428,7 +430,7 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
           if (kR1) tau_in *= corr;
           if (kLls == 2) {
             const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
-            tau_in = fma((double)P.lls_grid[xfast_index(P, F.p, cell)] * P.sigma_HI, pathc, tau_in);
+            tau_in = fma((double)P.lls_grid[xfast_index(P, F.lay, cell)] * P.sigma_HI, pathc, tau_in);
           } else if (kLls == 1) {
             tau_in = fma(P.tau_lls, pathc, tau_in);
           }
@@ -441,7 +443,7 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
           const int j = j0 + jj;
           if ((ownmask >> j) & 1u) {
             const unsigned cell = ((j & 1) ? baseAm : baseAp) + ((j & 2) ? cellm : cellp);
-            if (kDebug) P.coldens_dbg[xfast_index(P, F.p, cell)] = out.v[j] * P.inv_sigma;
+            if (kDebug) P.coldens_dbg[xfast_index(P, F.lay, cell)] = out.v[j] * P.inv_sigma;
             if (!(tin[jj] > P.tau_stop) && !stop_all) {    // evolve_point.F90:201
               const double tau_cell = tc.v[j];
               double phi_all, phi_out, heat_all = 0.0;
@@ -472,12 +474,14 @@ __device__ __forceinline__ void trace_shell(const RtParams& P, const SrcCtx& S, 
 
 // per-face constants of one subbox pass.  face f: p = f mod 3 (0: z, 1: y, 2: x principal), positive side first.
 // axes: p==0: (P,A,B)=(z,x,y); p==1: (y,x,z); p==2: (x,y,z) on the y-fastest twins (index (x*n2+z)*n1+y)
+// kTwins = false: the x-principal faces address the x-fastest grids too (a = y has stride n0, b = z has n0*n1)
+template <bool kTwins>
 __device__ __forceinline__ Face make_face(const RtParams& P, int f, int src0, int src1, int src2, int lr0, int ll0,
                                           int lr1, int ll1, int lr2, int ll2) {
   const int p = (f >= 3) ? f - 3 : f, sp = (f >= 3) ? -1 : 1;
   const int n0 = P.n[0], n1 = P.n[1], n2 = P.n[2];
   Face F;
-  F.p = p; F.sp = sp; F.pad_ = 0;
+  F.p = p; F.sp = sp; F.strA = 1u; F.lay = (kTwins && p == 2) ? 2 : 0;
   F.srcP = (p == 0) ? src2 : (p == 1 ? src1 : src0);
   F.srcA = (p == 2) ? src1 : src0;
   F.srcB = (p == 0) ? src1 : src2;
@@ -496,6 +500,10 @@ __device__ __forceinline__ Face make_face(const RtParams& P, int f, int src0, in
   F.tau = (p == 2) ? P.tau_cell_t : P.tau_cell;
   F.phih = (p == 2) ? P.phih_t : P.phih;
   F.heat = (p == 2) ? P.phiheat_t : P.phiheat;
+  if (!kTwins && p == 2) {
+    F.strP = 1u; F.strA = (unsigned)n0; F.strB = (unsigned)n0 * (unsigned)n1;
+    F.tau = P.tau_cell; F.phih = P.phih; F.heat = P.phiheat;
+  }
   return F;
 }
 
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       lr1 = min(reach, P.lim[1][1]); ll1 = min(reach, P.lim[1][0]);
       lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
       const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
-      if (tid < kNf) s_face[tid] = make_face(P, (int)crank * kNf + tid, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2);
+      if (tid < kNf) s_face[tid] = make_face<true>(P, (int)crank * kNf + tid, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2);
       double loss = 0.0;
       if (r_done < 0) {
         // shell 0 = the source cell (evolve_point.F90:151-160): coldensh_in=0, path=dr/2, vol_ph=cell volume.
@@ -720,24 +728,25 @@ __global__ void __launch_bounds__(32 * kWarpMax, 1) raytrace_warp_kernel(RtParam
   __shared__ Face s_face[kWarpMax][kFaces];
   __shared__ int s_next[kWarpMax];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
-  const int cap = P.warp_plane_doubles;
+  const int cap0 = P.warp_plane_doubles[0], cap1 = P.warp_plane_doubles[1];   // planes of the even / odd shells
   for (int i = tid; i < kTableLen; i += nthreads) s_thick[i] = P.thick2[i];
   for (int i = tid; i < 128; i += nthreads) s_logtab[i] = P.logtab[i];
   if (kHeat)
     for (int i = tid; i < kTableLen; i += nthreads) s_heat[i] = P.heat2[i];
-  const int per_warp = 2 * kFaces * (cap + kPadFront);
+  const int sstride = cap0 + cap1 + 2 * kPadFront;   // from a face's two buffers to the next face's
+  const int per_warp = kFaces * sstride;
   for (int i = tid; i < (nthreads >> 5) * per_warp; i += nthreads) s_planes[i] = 0.0;
   __syncthreads();
   double* wbase = s_planes + (size_t)wid * per_warp;
   double* sbuf0 = wbase + kPadFront;
-  double* sbuf1 = sbuf0 + cap + kPadFront;
-  const int sstride = 2 * (cap + kPadFront);
+  double* sbuf1 = sbuf0 + cap0 + kPadFront;
   LogC L;
   L.c0 = P.logc[0]; L.c1 = P.logc[1]; L.c2 = P.logc[2]; L.c3 = P.logc[3]; L.c4 = P.logc[4]; L.B = P.logB;
   SrcCtx S;
   S.rsafe = min(min(min(P.lim[0][0], P.lim[0][1]), min(P.lim[1][0], P.lim[1][1])), min(P.lim[2][0], P.lim[2][1]));
   const int reach = P.subboxsize;   // nbox = 1; the host guarantees reach < rsafe
   S.reach = reach;
+  const int dead_hi = __double2hiint(P.tau_stop * 1.000001) + 1;
   for (;;) {
     int w = 0;
     if (lane == 0) w = (int)atomicAdd(P.ticket, 1u);
@@ -756,13 +765,13 @@ __global__ void __launch_bounds__(32 * kWarpMax, 1) raytrace_warp_kernel(RtParam
       continue;
     }
     __syncwarp();   // the lanes are done with the previous source's faces and planes
-    if (lane < kFaces) s_face[wid][lane] = make_face(P, lane, src0, src1, src2, reach, reach, reach, reach, reach, reach);
+    if (lane < kFaces) s_face[wid][lane] = make_face<false>(P, lane, src0, src1, src2, reach, reach, reach, reach, reach, reach);
     if (lane < 4 * kFaces) {
       // shell 0 = the source cell (evolve_point.F90:151-160), plane 0 of every quadrant
       const unsigned cell = ((unsigned)src2 * (unsigned)P.n[1] + (unsigned)src1) * (unsigned)P.n[0] + (unsigned)src0;
       const double tau_cell = P.tau_cell[cell];
       const double tau_out = 0.5 * tau_cell;
-      wbase[(size_t)(2 * (lane >> 2)) * (cap + kPadFront) + kPadFront + (lane & 3)] = tau_out;
+      sbuf0[(lane >> 2) * sstride + (lane & 3)] = tau_out;
       if (lane == 0) {
         double phi_all, phi_out, heat_all = 0.0;
         photo_rates<kHeat>(0.0, tau_out, S.normflux, s_thick, s_logtab, s_heat, P, L, phi_all, phi_out, heat_all);
@@ -775,8 +784,8 @@ __global__ void __launch_bounds__(32 * kWarpMax, 1) raytrace_warp_kernel(RtParam
       }
     }
     double loss = 0.0;
-    int min_hi = 0x7fffffff;
     for (int r = 1; r <= reach; ++r) {
+      int min_hi = 0x7fffffff;   // high word of the smallest optical depth written to plane r
       if (lane == 0) s_next[wid] = 0;
       __syncwarp();   // plane r-1, the faces and the work counter are visible to the warp
       double* cur = (r & 1) ? sbuf1 : sbuf0;
@@ -784,6 +793,9 @@ __global__ void __launch_bounds__(32 * kWarpMax, 1) raytrace_warp_kernel(RtParam
       const int nseg = P.nseg_w[r];
       if (r == 1) trace_shell<kFaces, 32, false, false, true, kLls, false, kHeat>(P, S, s_face[wid], lane, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[wid], loss, min_hi);
       else trace_shell<kFaces, 32, false, false, false, kLls, false, kHeat>(P, S, s_face[wid], lane, s_thick, s_logtab, s_heat, L, r, prev, cur, sstride, nseg, &s_next[wid], loss, min_hi);
+      // dead-shell rule (see raytrace_kernel): once every optical depth of plane r exceeds the 2e19 column by a
+      // margin, no later cell of this source has a rate or a boundary loss; the cells still count as updates
+      if (__reduce_min_sync(0xffffffffu, min_hi) > dead_hi) break;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
@@ -929,12 +941,14 @@ int raytrace_configure(int max_radius, bool heat_tables, int subboxsize, int min
   info->grid_max = info->grid_cta + info->clusters;
   // per-warp kernel: shells 0..subboxsize of one source per warp, planes of every warp in shared memory
   info->warp_warps = 0;
-  info->warp_plane_doubles = 0;
+  info->warp_plane_doubles[0] = info->warp_plane_doubles[1] = 0;
   info->grid_warp = sms;
   if (subboxsize >= 1 && subboxsize < min_lim) {
-    const int P1 = subboxsize + 1;
-    const int cap_w = (4 * P1 * P1 + 4 * P1 + 8 + 3) & ~3;
-    const size_t per_warp = (size_t)2 * kFaces * (cap_w + kPadFront) * sizeof(double);
+    // shells alternate between two buffers per face: even r in the first, odd r in the second
+    auto plane_cap = [](int r) { const int P1 = r + 1; return (4 * P1 * P1 + 4 * P1 + 8 + 3) & ~3; };
+    const int r_even = subboxsize & ~1, r_odd = (subboxsize - 1) | 1;
+    const int cap_e = plane_cap(r_even), cap_o = plane_cap(r_odd);
+    const size_t per_warp = (size_t)kFaces * (cap_e + cap_o + 2 * kPadFront) * sizeof(double);
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, pick_warp_kernel(1, heat_tables)) != cudaSuccess) return (int)cudaGetLastError();
     const long room = (long)max_optin - (long)fa.sharedSizeBytes - (long)fixed - 256;
@@ -949,7 +963,8 @@ int raytrace_configure(int max_radius, bool heat_tables, int subboxsize, int min
           if (e2 != cudaSuccess) return (int)e2;
         }
       info->warp_warps = nw;
-      info->warp_plane_doubles = cap_w;
+      info->warp_plane_doubles[0] = cap_e;
+      info->warp_plane_doubles[1] = cap_o;
     }
   }
   return 0;
@@ -993,7 +1008,7 @@ void launch_raytrace(const RtParams& p, int grid, cudaStream_t stream) {
 void launch_raytrace_warp(const RtParams& p, int grid, int warps, cudaStream_t stream) {
   const bool heat = p.phiheat != nullptr;
   const size_t smem = (size_t)(kTableLen + 128 + (heat ? kTableLen : 0)) * sizeof(double2) +
-                      (size_t)warps * 2 * kFaces * (p.warp_plane_doubles + kPadFront) * sizeof(double);
+                      (size_t)warps * kFaces * (p.warp_plane_doubles[0] + p.warp_plane_doubles[1] + 2 * kPadFront) * sizeof(double);
   pick_warp_kernel(lls_mode(p), heat)<<<grid, 32 * warps, smem, stream>>>(p);
 }
 
