@@ -742,6 +742,7 @@ static void fill_chem(c2b_handle* h, double dt, ChemParams& cp) {
   cp.clumping_grid = (c.type_of_clumping >= 3) ? h->d_clump : nullptr;
   cp.clumping = h->clumping;
   cp.dt = dt;
+  cp.inv_dt = dt > 0.0 ? 1.0 / dt : 0.0;
   const double T = h->temper_val;
   cp.bh00 = c.bh00;
   cp.powT = std::pow(T / (double)1e4f, c.albpow);   // (temp0/1e4)**albpow, doric.f90:74

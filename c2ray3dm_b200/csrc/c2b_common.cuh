@@ -112,7 +112,7 @@ struct ChemParams {
   const double* phih;
   const float* clumping_grid;  // type 3/4/5 or nullptr
   float clumping;              // scalar (default real, clumping_module.F90:17)
-  double dt;
+  double dt, inv_dt;       // inv_dt = 1/dt (0 when dt == 0: statistics-only launches)
   double bh00_powT;        // bh00*(T/1e4)**albpow is formed as (clumping*bh00)*powT, doric.f90:74
   double bh00, powT;
   double acolh0;           // colh0*sqrt(T)*exp(-temph0/T), doric.f90:77

@@ -52,14 +52,26 @@ __device__ __forceinline__ void block_store(const Acc& a, double* partials) {
   }
 }
 
-// doric.f90:33-134 for the isothermal case; brech0 and acolh0 are cell-invariant up to clumping
-__device__ __forceinline__ void doric(double dt, double rhe, double brech0, double acolh0, double phih,
+// 1/x: hardware seed (>= 20 bits) refined with y*(1+e+e^2), e = 1-x*y  =>  relative error ~e^3 < 1e-17
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(t, y, y);
+}
+
+// doric.f90:33-134 for the isothermal case; brech0 and acolh0 are cell-invariant up to clumping.
+// The three divisions by delth (:88-89,117) share one reciprocal (an ulp-level difference; the parity bound on the
+// fractions is 1e-6); inv_dt = 1/dt.
+__device__ __forceinline__ void doric(double dt, double inv_dt, double rhe, double brech0, double acolh0, double phih,
                                       double eps, double xold1, double xold0, double& x1, double& x0,
                                       double& xav1, double& xav0) {
   const double aih0 = phih + rhe * acolh0;
   const double delth = aih0 + rhe * brech0;
-  const double eqxfh1 = aih0 / delth;
-  const double eqxfh0 = rhe * brech0 / delth;
+  const double inv_delth = fast_rcp(delth);
+  const double eqxfh1 = aih0 * inv_delth;
+  const double eqxfh0 = (rhe * brech0) * inv_delth;
   const double deltht = delth * dt;
   const double ee = exp(-deltht);
   x1 = (xold1 - eqxfh1) * ee + eqxfh1;
@@ -68,7 +80,7 @@ __device__ __forceinline__ void doric(double dt, double rhe, double brech0, doub
     x0 = eps;
     x1 = 1.0 - eps;
   }
-  const double avg_factor = (deltht < (double)1.0e-8f) ? 1.0 : (1.0 - ee) / deltht;
+  const double avg_factor = (deltht < (double)1.0e-8f) ? 1.0 : (1.0 - ee) * (inv_delth * inv_dt);
   xav1 = eqxfh1 + (xold1 - eqxfh1) * avg_factor;
   xav0 = 1.0 - xav1;
   if (xav0 < eps) xav0 = eps;
@@ -81,7 +93,7 @@ __device__ __forceinline__ void doric_T(const ChemParams& P, double temp0, float
                                         double& xav0) {
   const double brech0 = (double)clump * P.bh00 * pow(temp0 / (double)1e4f, P.albpow);   // doric.f90:74
   const double acolh0 = P.colh0 * sqrt(temp0) * exp(-P.temph0 / temp0);                 // :76-77
-  doric(P.dt, rhe, brech0, acolh0, phih, P.epsilon, xold1, xold0, x1, x0, xav1, xav0);
+  doric(P.dt, P.inv_dt, rhe, brech0, acolh0, phih, P.epsilon, xold1, xold0, x1, x0, xav1, xav0);
 }
 
 // coolin, cooling.f90:38-59 (the 61-entry CIE curve sits in shared memory)
@@ -132,6 +144,52 @@ __device__ __forceinline__ void thermal(const ChemParams& P, const double* s_coo
   final_temperature = internal_energy * P.gamma1 / (P.k_B * (ndens_atom + ndens_atom * (h1 + P.abu_c)));
 }
 
+// what follows the do_chemistry loop for one cell: set_temperature_point, the convergence test against the previous
+// iterate (evolve_point.F90:378-401), the opacity for the next ray trace and the fused reductions
+template <bool kThermal>
+__device__ __forceinline__ void chem_finish(const ChemParams& P, size_t c, double xav_prev, double ndens_p, float clump,
+                                            double h1, double h_av1, double h_av0, double T_start_avg, double T_end_avg,
+                                            double T_end_int, double& out_intermed, double& out_av, double& out_tau,
+                                            Acc& acc) {
+  double T_new_avg = 0.0;
+  if (kThermal) {   // set_temperature_point (:553): intermed and average, stored as default real
+    const float fa = (float)T_end_avg;
+    P.T_int[c] = (float)T_end_int;
+    P.T_avg[c] = fa;
+    T_new_avg = (double)fa;
+  }
+  // convergence against the previous iterate, evolve_point.F90:378-391
+  const double yh0_prev = 1.0 - fmax(P.epsilon, xav_prev);
+  const double dabs = fabs(h_av0 - yh0_prev);
+  bool unconverged = dabs > P.minimum_fractional_change &&
+                     dabs > P.minimum_fractional_change * h_av0 &&   // abs((yh_av(0)-yh0_av_old)/yh_av(0)) > ..., :380
+                     h_av0 > P.minimum_fraction_of_atoms;
+  if (kThermal)
+    unconverged = unconverged || (fabs((T_start_avg - T_new_avg) / T_new_avg) > 1.0e-1 &&
+                                  fabs(T_start_avg - T_new_avg) > 100.0);
+  if (unconverged) acc.conv += 1.0;
+  out_intermed = h1;  // :400-401
+  out_av = h_av1;
+  // opacity grid for the next ray trace: the h_av(0) evolve0D will form from this xh_av
+  // (evolve_point.F90:137-142) times ndens times sigma_HI*dr(1)
+  out_tau = P.sigma_dr0 * (fmax(1.0 - fmax(h_av1, P.epsilon), P.epsilon) * ndens_p);
+  // fused reductions
+  acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
+  acc.sum_x += h1;                                       // :565
+  acc.h0 += ndens_p * (1.0 - h1);                        // state_after(xh_intermed)
+  acc.h1 += ndens_p * h1;
+  const double yh1 = h_av1, yh0 = 1.0 - h_av1;           // total_rates(dt,xh_av)
+  const double ne = ndens_p * (yh1 + P.abu_c);
+  if (kThermal) {   // temperature%average of the cell, photonstatistics.F90:166-176
+    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * pow(T_new_avg / (double)1e4f, P.albpow);
+    acc.coll += ndens_p * yh0 * ne * P.colh0 * sqrt(T_new_avg) * exp(-P.temph0 / T_new_avg);
+  } else {
+    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
+    acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
+  }
+}
+
+
 // one cell of global_pass: evolve0D_global + do_chemistry (evolve_point.F90:305-555) and the fused reductions
 template <bool kThermal>
 __device__ __forceinline__ void chem_cell(const ChemParams& P, const double* s_cool, size_t c, double xh_c,
@@ -165,49 +223,16 @@ __device__ __forceinline__ void chem_cell(const ChemParams& P, const double* s_c
       de = ndens_p * (h_av1 + P.abu_c);
       thermal(P, s_cool, T_start_cur, T_end_int, T_end_avg, de, ndens_p, h1, h_old1, h_av1, heat);   // :519-526
     } else {
-      doric(P.dt, de, brech0, P.acolh0, phih, P.epsilon, h_old1, h_old0, h1, h0, h_av1, h_av0);
+      doric(P.dt, P.inv_dt, de, brech0, P.acolh0, phih, P.epsilon, h_old1, h_old0, h1, h0, h_av1, h_av0);
     }
     // (the temperature term of :530-535 compares temperature_end%current, which never changes)
-    if (fabs((h_av0 - yh0_av_old) / h_av0) < P.minimum_fractional_change || h_av0 < P.minimum_fraction_of_atoms)
+    // abs((yh_av(0)-yh0_av_old)/yh_av(0)) < minimum_fractional_change (evolve_point.F90:530), yh_av(0) > 0
+    if (fabs(h_av0 - yh0_av_old) < P.minimum_fractional_change * h_av0 || h_av0 < P.minimum_fraction_of_atoms)
       break;
     if (nit > 400) break;  // 'Convergence failing (global)'
   }
-  double T_new_avg = 0.0;
-  if (kThermal) {   // set_temperature_point (:553): intermed and average, stored as default real
-    const float fa = (float)T_end_avg;
-    P.T_int[c] = (float)T_end_int;
-    P.T_avg[c] = fa;
-    T_new_avg = (double)fa;
-  }
-  // convergence against the previous iterate, evolve_point.F90:378-391
-  const double yh0_prev = 1.0 - fmax(P.epsilon, xav_prev);
-  const double dabs = fabs(h_av0 - yh0_prev);
-  bool unconverged = dabs > P.minimum_fractional_change &&
-                     fabs((h_av0 - yh0_prev) / h_av0) > P.minimum_fractional_change &&
-                     h_av0 > P.minimum_fraction_of_atoms;
-  if (kThermal)
-    unconverged = unconverged || (fabs((T_start_avg - T_new_avg) / T_new_avg) > 1.0e-1 &&
-                                  fabs(T_start_avg - T_new_avg) > 100.0);
-  if (unconverged) acc.conv += 1.0;
-  out_intermed = h1;  // :400-401
-  out_av = h_av1;
-  // opacity grid for the next ray trace: the h_av(0) evolve0D will form from this xh_av
-  // (evolve_point.F90:137-142) times ndens times sigma_HI*dr(1)
-  out_tau = P.sigma_dr0 * (fmax(1.0 - fmax(h_av1, P.epsilon), P.epsilon) * ndens_p);
-  // fused reductions
-  acc.maxav = fmax(acc.maxav, xav_prev);                 // evolve.F90:535 (before the pass)
-  acc.sum_x += h1;                                       // :565
-  acc.h0 += ndens_p * (1.0 - h1);                        // state_after(xh_intermed)
-  acc.h1 += ndens_p * h1;
-  const double yh1 = h_av1, yh0 = 1.0 - h_av1;           // total_rates(dt,xh_av)
-  const double ne = ndens_p * (yh1 + P.abu_c);
-  if (kThermal) {   // temperature%average of the cell, photonstatistics.F90:166-176
-    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * pow(T_new_avg / (double)1e4f, P.albpow);
-    acc.coll += ndens_p * yh0 * ne * P.colh0 * sqrt(T_new_avg) * exp(-P.temph0 / T_new_avg);
-  } else {
-    acc.rec += ndens_p * yh1 * ne * (double)clump * P.bh00 * P.powT;
-    acc.coll += ndens_p * yh0 * ne * P.colh0 * P.sqrtT * P.expT;  // photonstatistics.F90:174-177
-  }
+  chem_finish<kThermal>(P, c, xav_prev, ndens_p, clump, h1, h_av1, h_av0, T_start_avg, T_end_avg, T_end_int,
+                        out_intermed, out_av, out_tau, acc);
 }
 
 // Two cells per thread: every grid is read and written with 128-bit (double2) / 64-bit (float2) accesses.
@@ -233,6 +258,8 @@ __global__ void __launch_bounds__(kThreads) chemistry_kernel(ChemParams P) {
     const float2 nd = nd2[i];
     const float2 cl = P.clumping_grid ? cl2[i] : make_float2(P.clumping, P.clumping);  // clumping_point
     double2 oi, oa, ot;
+    // (the two cells one after the other: iterating them in lockstep for instruction-level parallelism doubles the
+    // registers and measured slower, 205 vs 162 us per launch at 256^3, than 32 resident warps of this form)
     chem_cell<kThermal>(P, s_cool, 2 * i, x.x, xa.x, ph.x, nd.x, cl.x, oi.x, oa.x, ot.x, acc);
     chem_cell<kThermal>(P, s_cool, 2 * i + 1, x.y, xa.y, ph.y, nd.y, cl.y, oi.y, oa.y, ot.y, acc);
     xint2[i] = oi;
