@@ -85,6 +85,10 @@ struct c2b_handle {
   int* d_ovf = nullptr;        // sources the per-warp kernel hands over to the single-CTA kernel
   int warp_min_sources = 0;    // the per-warp kernel is used when at least this many sources qualify
   unsigned int* h_ovf = nullptr;   // pinned: number of handed-over sources of the last pass
+  // the three work lists of the last pass: they stay on the device while no source's predicted length changes
+  bool routes_valid = false;
+  int n_small = 0, n_large = 0, n_tiny = 0;
+  std::vector<int64_t> updates_of_nbox;   // cells of the final subbox for nbox = 0, 1, 2, ...
   long long route_counts[4] = {0, 0, 0, 0};
   int *d_nseg_cta = nullptr, *d_nseg_cl = nullptr, *d_nseg_w = nullptr;
   std::vector<int> nbox_pred;  // per source: nbox of the previous trace (routing + longest-first order)
@@ -586,6 +590,7 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   // do ns1=1+rank,NumSrc,npr (master_slave.F90:85)
   for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
   h->nwork = (int)h->work.size();
+  h->routes_valid = false;
   h->nbox_pred.assign((size_t)NumSrc, 0);
   if (same_sources) h->nbox_pred = kept_pred;
   {
@@ -1017,6 +1022,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     // source already fills the GPU and has less synchronisation, so the cluster kernel is used only
     // while the long traces are few.  Sources never traced before (prediction 0) count as long when the
     // whole list is short.
+    if (!h->routes_valid) {
     std::vector<int> small, large, tiny;
     const bool few = (int)h->work.size() <= h->cluster_max_sources;
     const bool zorder = !(getenv("C2B_NO_ZORDER") && atoi(getenv("C2B_NO_ZORDER")));
@@ -1056,13 +1062,17 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       CU(h, cudaMemcpyAsync(h->d_work, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (!large.empty())
       CU(h, cudaMemcpyAsync(h->d_work2, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    if (int rc = trace_sources(h, h->d_work, (int)small.size(), h->d_work2, (int)large.size(), h->d_work3, (int)tiny.size(), 0, nullptr, 0)) return rc;
+    h->n_small = (int)small.size(); h->n_large = (int)large.size(); h->n_tiny = (int)tiny.size();
+    h->routes_valid = true;
+    }
+    const int n_small = h->n_small, n_large = h->n_large, n_tiny = h->n_tiny;
+    if (int rc = trace_sources(h, h->d_work, n_small, h->d_work2, n_large, h->d_work3, n_tiny, 0, nullptr, 0)) return rc;
     CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_ovf, h->d_ticket + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventElapsedTime(&ms_rt, h->ev[0], h->ev[1]));
-    if (small.empty() && !tiny.empty() && *h->h_ovf > 0u) {
+    if (n_small == 0 && n_tiny > 0 && *h->h_ovf > 0u) {
       // only the per-warp kernel ran and some of its sources need more than one subbox: the single-CTA kernel
       // carries on with those (when the single-CTA kernel runs in the same pass it takes them there and then)
       if (int rc = trace_sources(h, nullptr, 0, nullptr, 0, nullptr, 0, (int)*h->h_ovf, nullptr, 4)) return rc;
@@ -1073,16 +1083,22 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       CU(h, cudaEventElapsedTime(&ms2, h->ev[4], h->ev[5]));
       ms_rt += ms2;
     }
-    h->route_counts[0] += (long long)small.size();
-    h->route_counts[1] += (long long)large.size();
-    h->route_counts[2] += (long long)tiny.size();
+    h->route_counts[0] += (long long)n_small;
+    h->route_counts[1] += (long long)n_large;
+    h->route_counts[2] += (long long)n_tiny;
     h->route_counts[3] += (long long)*h->h_ovf;
     // photon_loss(1)=photon_loss(1)+photon_loss_src ; sum_nbox=sum_nbox+nbox, in source order
     for (int w : h->work) {
-      h->nbox_pred[w] = h->h_nbox[w];
+      const int nb = h->h_nbox[w];
+      if (nb != h->nbox_pred[w]) {
+        h->nbox_pred[w] = nb;
+        h->routes_valid = false;   // the next pass sorts and routes again
+      }
       loss_sum = loss_sum + h->h_loss[w];
-      nbox_sum += (double)h->h_nbox[w];
-      upd_sum += (double)box_updates(h, h->h_nbox[w]);
+      nbox_sum += (double)nb;
+      if ((size_t)nb >= h->updates_of_nbox.size())
+        for (int k = (int)h->updates_of_nbox.size(); k <= nb; ++k) h->updates_of_nbox.push_back(box_updates(h, k));
+      upd_sum += (double)h->updates_of_nbox[(size_t)nb];
     }
   }
   if (h->cfg.nranks > 1) {
