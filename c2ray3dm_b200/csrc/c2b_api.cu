@@ -104,6 +104,13 @@ struct c2b_handle {
   double* d_loss = nullptr;
   int* h_nbox = nullptr;      // pinned
   double* h_loss = nullptr;   // pinned
+  // multi-rank load balance: which rank traces which source in the next pass (the static round-robin of
+  // master_slave.F90:85 until the trace lengths and the ranks' measured speeds are known)
+  std::vector<int> owner;          // per source
+  std::vector<int> morton_all;     // all sources in Z-order of their mesh position
+  std::vector<double> rank_speed;  // updates per ms of every rank's last ray-trace pass (as dealt with)
+  bool balance = false;            // nranks > 1 and not disabled
+  int* h_nbox_all = nullptr;       // pinned: nbox of every source after the all-reduce
   std::vector<int> work;      // 0-based source indices of this rank
   std::vector<int> work_morton;  // the same indices in Z-order of their mesh position (L2 locality of concurrent traces)
   std::vector<int> srcpos;
@@ -364,9 +371,10 @@ int c2b_create(const c2b_config* cfg, c2b_handle** out) {
   if ((e = cudaMalloc(&h->d_partials, (size_t)h->chem_blocks * kNumStat * sizeof(double))) != cudaSuccess)
     return bail("cudaMalloc", e);
   if ((e = cudaMalloc(&h->d_stats, kNumStat * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
-  if ((e = cudaMalloc(&h->d_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+  const size_t nsmall = 4 + 2 * (size_t)cfg->nranks;   // {loss, nbox, updates, -} + {ms, updates} of every rank
+  if ((e = cudaMalloc(&h->d_small, nsmall * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMallocHost(&h->h_stats, kNumStat * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
-  if ((e = cudaMallocHost(&h->h_small, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
+  if ((e = cudaMallocHost(&h->h_small, nsmall * sizeof(double))) != cudaSuccess) return bail("cudaMallocHost", e);
   if ((e = cudaMallocHost(&h->h_ovf, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMallocHost", e);
   *h->h_ovf = 0u;
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail("sync", e);
@@ -389,6 +397,7 @@ void c2b_destroy(c2b_handle* h) {
   cudaFree(h->d_scratch); cudaFree(h->d_partials); cudaFree(h->d_stats); cudaFree(h->d_small);
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
+  if (h->h_nbox_all) cudaFreeHost(h->h_nbox_all);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->h_small) cudaFreeHost(h->h_small);
   if (h->h_ovf) cudaFreeHost(h->h_ovf);
@@ -562,6 +571,41 @@ int c2b_set_temperature(c2b_handle* h, double t) {
   return 0;
 }
 
+// Deals sources to ranks for one pass: cost[s] = predicted updates of source s, speed[r] = relative speed of rank r.
+// Longest trace first, each to the rank that is furthest below its share speed[r]/sum(speed) of the total cost
+// (ties: the lower rank).  Deterministic: every rank computes the same assignment from the same all-reduced inputs.
+int c2b_deal_sources(int32_t nsrc, const int64_t* cost, int32_t nranks, const double* speed, int32_t* owner) {
+  if (nsrc < 0 || nranks < 1 || (nsrc > 0 && (!cost || !owner))) return 1;
+  double stot = 0.0, ctot = 0.0;
+  for (int r = 0; r < nranks; ++r) stot += (speed && speed[r] > 0.0) ? speed[r] : 1.0;
+  for (int s = 0; s < nsrc; ++s) ctot += (double)std::max<int64_t>(cost[s], 1);
+  std::vector<double> deficit((size_t)nranks);
+  for (int r = 0; r < nranks; ++r) deficit[(size_t)r] = ctot * ((speed && speed[r] > 0.0) ? speed[r] : 1.0) / stot;
+  std::vector<int> order((size_t)nsrc);
+  for (int s = 0; s < nsrc; ++s) order[(size_t)s] = s;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  for (int s : order) {
+    int best = 0;
+    for (int r = 1; r < nranks; ++r)
+      if (deficit[(size_t)r] > deficit[(size_t)best]) best = r;
+    owner[s] = best;
+    deficit[(size_t)best] -= (double)std::max<int64_t>(cost[s], 1);
+  }
+  return 0;
+}
+
+// this rank's sources from h->owner, in source order (work) and in Z-order (work_morton)
+static void rebuild_work(c2b_handle* h) {
+  h->work.clear();
+  h->work_morton.clear();
+  for (int s = 0; s < h->NumSrc; ++s)
+    if (h->owner[(size_t)s] == h->cfg.rank) h->work.push_back(s);
+  for (int s : h->morton_all)
+    if (h->owner[(size_t)s] == h->cfg.rank) h->work_morton.push_back(s);
+  h->nwork = (int)h->work.size();
+  h->routes_valid = false;
+}
+
 int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const double* nf, double S_star) {
   C2B_CHECK_H(h);
   if (NumSrc < 0) return fail(h, "c2b_set_sources: negative NumSrc");
@@ -576,21 +620,24 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   h->d_srcpos = nullptr; h->d_normflux = nullptr; h->d_work = nullptr; h->d_nbox = nullptr; h->d_loss = nullptr;
   if (h->h_nbox) cudaFreeHost(h->h_nbox);
   if (h->h_loss) cudaFreeHost(h->h_loss);
-  h->h_nbox = nullptr; h->h_loss = nullptr;
+  if (h->h_nbox_all) cudaFreeHost(h->h_nbox_all);
+  h->h_nbox = nullptr; h->h_loss = nullptr; h->h_nbox_all = nullptr;
   // the same source list again (a host that re-sends its state every step): keep the per-source trace lengths
   // the work queue is ordered by
   const bool same_sources = NumSrc == h->NumSrc && NumSrc > 0 && (int)h->nbox_pred.size() == NumSrc &&
                             std::equal(srcpos, srcpos + 3 * (size_t)NumSrc, h->srcpos.begin());
-  std::vector<int> kept_pred;
+  std::vector<int> kept_pred, kept_owner;
   if (same_sources) kept_pred = h->nbox_pred;
+  if (same_sources && (int)h->owner.size() == NumSrc) kept_owner = h->owner;
   h->NumSrc = NumSrc;
   h->S_star = S_star;
-  h->work.clear();
   h->srcpos.assign(srcpos, srcpos + 3 * (size_t)NumSrc);
   // do ns1=1+rank,NumSrc,npr (master_slave.F90:85)
-  for (int ns1 = 1 + h->cfg.rank; ns1 <= NumSrc; ns1 += h->cfg.nranks) h->work.push_back(ns1 - 1);
-  h->nwork = (int)h->work.size();
-  h->routes_valid = false;
+  h->owner.assign((size_t)NumSrc, 0);
+  for (int s = 0; s < NumSrc; ++s) h->owner[(size_t)s] = s % h->cfg.nranks;
+  if (!kept_owner.empty()) h->owner = kept_owner;
+  h->balance = h->cfg.nranks > 1 && !(getenv("C2B_NO_BALANCE") && atoi(getenv("C2B_NO_BALANCE")));
+  if (h->rank_speed.size() != (size_t)h->cfg.nranks) h->rank_speed.assign((size_t)h->cfg.nranks, 1.0);
   h->nbox_pred.assign((size_t)NumSrc, 0);
   if (same_sources) h->nbox_pred = kept_pred;
   {
@@ -606,30 +653,33 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
       return v;
     };
     std::vector<std::pair<unsigned long long, int>> keyed;
-    keyed.reserve(h->work.size());
-    for (int w : h->work) {
+    keyed.reserve((size_t)NumSrc);
+    for (int w = 0; w < NumSrc; ++w) {
       const unsigned long long k = spread((unsigned)(srcpos[3 * w] - 1) >> 3) | (spread((unsigned)(srcpos[3 * w + 1] - 1) >> 3) << 1) |
                                    (spread((unsigned)(srcpos[3 * w + 2] - 1) >> 3) << 2);
       keyed.emplace_back(k, w);
     }
     std::stable_sort(keyed.begin(), keyed.end());
-    h->work_morton.clear();
-    for (auto& kw : keyed) h->work_morton.push_back(kw.second);
+    h->morton_all.clear();
+    for (auto& kw : keyed) h->morton_all.push_back(kw.second);
   }
+  rebuild_work(h);
   h->sum_normflux = 0.0;
   for (int s = 0; s < NumSrc; ++s) h->sum_normflux = h->sum_normflux + nf[s];  // sum(NormFlux_stellar(1:NumSrc))
   if (NumSrc == 0) return 0;
   const size_t ns = (size_t)NumSrc;
   CU(h, cudaMalloc(&h->d_srcpos, 3 * ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_normflux, ns * sizeof(double)));
-  CU(h, cudaMalloc(&h->d_work, std::max<size_t>(1, h->work.size()) * sizeof(int)));
-  CU(h, cudaMalloc(&h->d_work2, std::max<size_t>(1, h->work.size()) * sizeof(int)));
-  CU(h, cudaMalloc(&h->d_work3, std::max<size_t>(1, h->work.size()) * sizeof(int)));
-  CU(h, cudaMalloc(&h->d_ovf, std::max<size_t>(1, h->work.size()) * sizeof(int)));
+  // (any rank may be dealt any number of the sources)
+  CU(h, cudaMalloc(&h->d_work, ns * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_work2, ns * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_work3, ns * sizeof(int)));
+  CU(h, cudaMalloc(&h->d_ovf, ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_nbox, ns * sizeof(int)));
   CU(h, cudaMalloc(&h->d_loss, ns * sizeof(double)));
   CU(h, cudaMallocHost(&h->h_nbox, ns * sizeof(int)));
   CU(h, cudaMallocHost(&h->h_loss, ns * sizeof(double)));
+  CU(h, cudaMallocHost(&h->h_nbox_all, ns * sizeof(int)));
   CU(h, cudaMemcpyAsync(h->d_srcpos, srcpos, 3 * ns * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_normflux, nf, ns * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (!h->work.empty())
@@ -638,6 +688,7 @@ int c2b_set_sources(c2b_handle* h, int32_t NumSrc, const int32_t* srcpos, const 
   CU(h, cudaMemsetAsync(h->d_loss, 0, ns * sizeof(double), h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   memset(h->h_nbox, 0, ns * sizeof(int));
+  memset(h->h_nbox_all, 0, ns * sizeof(int));
   memset(h->h_loss, 0, ns * sizeof(double));
   return 0;
 }
@@ -1090,7 +1141,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     // photon_loss(1)=photon_loss(1)+photon_loss_src ; sum_nbox=sum_nbox+nbox, in source order
     for (int w : h->work) {
       const int nb = h->h_nbox[w];
-      if (nb != h->nbox_pred[w]) {
+      if (!h->balance && nb != h->nbox_pred[w]) {   // (with several ranks: below, from the all-reduced counts)
         h->nbox_pred[w] = nb;
         h->routes_valid = false;   // the next pass sorts and routes again
       }
@@ -1104,16 +1155,66 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
   if (h->cfg.nranks > 1) {
     // mpi_accumulate_grid_quantities, evolve.F90:577-616
     CU(h, cudaEventRecord(h->ev[2], h->stream));
+    const int nr = h->cfg.nranks;
+    const size_t nsmall = 4 + 2 * (size_t)nr;
     h->h_small[0] = loss_sum; h->h_small[1] = nbox_sum; h->h_small[2] = upd_sum; h->h_small[3] = 0.0;
-    CU(h, cudaMemcpyAsync(h->d_small, h->h_small, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (int r = 0; r < 2 * nr; ++r) h->h_small[4 + r] = 0.0;
+    h->h_small[4 + 2 * h->cfg.rank] = (double)ms_rt;       // how long this rank traced ...
+    h->h_small[5 + 2 * h->cfg.rank] = upd_sum;             // ... how many updates
+    CU(h, cudaMemcpyAsync(h->d_small, h->h_small, nsmall * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     NC(h, g_nccl.AllReduce(h->d_phih, h->d_phih, h->ncell, ncclDouble, ncclSum, h->comm, h->stream));
     if (h->d_phiheat)   // evolve.F90:604-609
       NC(h, g_nccl.AllReduce(h->d_phiheat, h->d_phiheat, h->ncell, ncclDouble, ncclSum, h->comm, h->stream));
-    NC(h, g_nccl.AllReduce(h->d_small, h->d_small, 4, ncclDouble, ncclSum, h->comm, h->stream));
-    CU(h, cudaMemcpyAsync(h->h_small, h->d_small, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    NC(h, g_nccl.AllReduce(h->d_small, h->d_small, nsmall, ncclDouble, ncclSum, h->comm, h->stream));
+    CU(h, cudaMemcpyAsync(h->h_small, h->d_small, nsmall * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->balance && h->NumSrc > 0) {
+      // every rank learns the subbox count of every source (each source was traced by exactly one rank)
+      NC(h, g_nccl.AllReduce(h->d_nbox, h->d_nbox, (size_t)h->NumSrc, ncclInt32, ncclSum, h->comm, h->stream));
+      CU(h, cudaMemcpyAsync(h->h_nbox_all, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
     CU(h, cudaEventRecord(h->ev[3], h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventElapsedTime(&ms_ar, h->ev[2], h->ev[3]));
+    if (h->balance && h->NumSrc > 0) {
+      // Deal the sources again for the next pass when a predicted trace length changed or a rank's measured speed
+      // moved by more than 2 %: the same inputs on every rank (all-reduced), so the same assignment everywhere.
+      bool redeal = false;
+      for (int s2 = 0; s2 < h->NumSrc; ++s2)
+        if (h->nbox_pred[(size_t)s2] != h->h_nbox_all[s2]) {
+          h->nbox_pred[(size_t)s2] = h->h_nbox_all[s2];
+          redeal = true;
+        }
+      // relative speeds (mean 1), half-way between the last deal's and this pass's measurement
+      std::vector<double> speed((size_t)nr, 0.0);
+      bool have_speed = true;
+      double ssum = 0.0;
+      for (int r = 0; r < nr; ++r) {
+        const double ms = h->h_small[4 + 2 * r], up = h->h_small[5 + 2 * r];
+        if (ms > 0.0 && up > 0.0) speed[(size_t)r] = up / ms;
+        else have_speed = false;
+        ssum += speed[(size_t)r];
+      }
+      if (have_speed) {
+        for (int r = 0; r < nr; ++r) {
+          speed[(size_t)r] = 0.5 * h->rank_speed[(size_t)r] + 0.5 * speed[(size_t)r] * nr / ssum;
+          if (std::fabs(speed[(size_t)r] - h->rank_speed[(size_t)r]) > 0.01) redeal = true;   // > 1 % of a fair share
+        }
+      }
+      if (redeal) {
+        if (have_speed) h->rank_speed = speed;
+        std::vector<int64_t> cost((size_t)h->NumSrc);
+        for (int s2 = 0; s2 < h->NumSrc; ++s2) {
+          const int nb = h->nbox_pred[(size_t)s2];
+          if ((size_t)nb >= h->updates_of_nbox.size())
+            for (int k = (int)h->updates_of_nbox.size(); k <= nb; ++k) h->updates_of_nbox.push_back(box_updates(h, k));
+          cost[(size_t)s2] = h->updates_of_nbox[(size_t)nb];
+        }
+        std::vector<int32_t> own((size_t)h->NumSrc);
+        c2b_deal_sources(h->NumSrc, cost.data(), nr, h->rank_speed.data(), own.data());
+        h->owner.assign(own.begin(), own.end());
+        rebuild_work(h);
+      }
+    }
     loss_sum = h->h_small[0]; nbox_sum = h->h_small[1]; upd_sum = h->h_small[2];
   }
   h->photon_loss = loss_sum;
@@ -1334,7 +1435,8 @@ int c2b_get_phih_f32(c2b_handle* h, float* p) {
 int c2b_get_source_nbox(c2b_handle* h, int32_t* nbox) {
   C2B_CHECK_H(h);
   if (!nbox) return fail(h, "c2b_get_source_nbox: null pointer");
-  if (h->NumSrc > 0) memcpy(nbox, h->h_nbox, (size_t)h->NumSrc * sizeof(int));
+  // with several ranks and the load balance on, every rank holds the all-reduced counts of all sources
+  if (h->NumSrc > 0) memcpy(nbox, h->balance ? h->h_nbox_all : h->h_nbox, (size_t)h->NumSrc * sizeof(int));
   return 0;
 }
 int c2b_get_source_loss(c2b_handle* h, double* loss) {
@@ -1445,6 +1547,13 @@ int c2b_get_route_counts(c2b_handle* h, int64_t counts[4]) {
   C2B_CHECK_H(h);
   if (!counts) return fail(h, "c2b_get_route_counts: null argument");
   for (int i = 0; i < 4; ++i) counts[i] = (int64_t)h->route_counts[i];
+  return 0;
+}
+
+int c2b_get_source_owner(c2b_handle* h, int32_t* owner) {
+  C2B_CHECK_H(h);
+  if (!owner && h->NumSrc > 0) return fail(h, "c2b_get_source_owner: null argument");
+  for (int s = 0; s < h->NumSrc; ++s) owner[s] = h->owner[(size_t)s];
   return 0;
 }
 

@@ -295,6 +295,12 @@ class Evolve:
         self._ck(self.L.c2b_measure_dfma_rate(self.h, C.byref(r)), "c2b_measure_dfma_rate")
         return r.value
 
+    def source_owner(self):
+        """rank that traces each source in the next pass (multi-rank load balance)"""
+        a = np.zeros(max(1, self.NumSrc), dtype=np.int32)
+        self._ck(self.L.c2b_get_source_owner(self.h, a.ctypes.data_as(C.POINTER(C.c_int32))), "c2b_get_source_owner")
+        return a[:self.NumSrc]
+
     def route_counts(self):
         """sources dealt so far to (one CTA, one cluster, one warp for the first subbox, handed over by the warp shape)"""
         a = (C.c_int64 * 4)()

@@ -187,7 +187,7 @@ int c2b_get_xh_intermed(c2b_handle *h, double *xh_intermed);
 int c2b_get_phih(c2b_handle *h, double *phih_grid);
 int c2b_get_phih_f32(c2b_handle *h, float *phih_grid_si);  /* real(phih_grid,si), output.F90:359 */
 int c2b_get_phiheat(c2b_handle *h, double *phiheat_grid);   /* evolve_data.F90:42 (non-isothermal) */
-int c2b_get_source_nbox(c2b_handle *h, int32_t *nbox /* NumSrc; 0 for sources of other ranks */);
+int c2b_get_source_nbox(c2b_handle *h, int32_t *nbox /* NumSrc; with nranks > 1 every rank holds the counts of all sources */);
 int c2b_get_source_loss(c2b_handle *h, double *loss /* NumSrc */);
 /* iteration dump / restart (evolve.F90:285-426): niter, photon_loss_all, phih, xh_av, xh_intermed */
 int c2b_get_iter_state(c2b_handle *h, int32_t *niter, double *photon_loss_all, double *phih_grid,
@@ -217,6 +217,15 @@ int c2b_measure_dfma_rate(c2b_handle *h, double *dfma_per_s);
  * [1] one cluster of 6 CTAs per source, [2] one warp per source for the first subbox, [3] of those, handed over to
  * the one-CTA shape because their loss still exceeded loss_fraction (evolve_source.F90:128-131) */
 int c2b_get_route_counts(c2b_handle *h, int64_t counts[4]);
+/* the rule that deals sources to ranks between passes when nranks > 1 (host logic, no device needed): cost[s] =
+ * predicted updates of source s, speed[r] = relative speed of rank r (null: all equal); longest trace first, each to
+ * the rank furthest below its share.  The first pass of a source list uses the reference's static rule
+ * ns = 1+rank, 1+rank+npr, ... (master_slave.F90:85); afterwards the library calls this with the all-reduced subbox
+ * counts and the ranks' measured ray-trace speeds (the reference's dynamic counterpart is do_grid_master,
+ * master_slave.F90:124-231). */
+int c2b_deal_sources(int32_t nsrc, const int64_t *cost, int32_t nranks, const double *speed, int32_t *owner);
+/* owner[s] = rank that traces source s in the next pass (NumSrc entries) */
+int c2b_get_source_owner(c2b_handle *h, int32_t *owner);
 
 #ifdef __cplusplus
 }

@@ -117,3 +117,36 @@ def test_synthetic_generators_are_deterministic():
     assert a[k - 1, j - 1, i - 1] == a.max()
     assert syn.avg_dens(9.0) == pytest.approx(1.9811847154954507e-4, rel=1e-12)
     assert syn.comoving_dr(128) == pytest.approx(3.4441966103425106e24, rel=1e-12)
+
+
+def test_deal_sources_rule():
+    """the host rule that deals sources to ranks between passes (multi-GPU load balance): every source to exactly
+    one rank, shares of the predicted cost proportional to the ranks' speeds, deterministic"""
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    n = 5000
+    cost = (rng.integers(1, 40, size=n).astype(np.int64)) ** 3
+    i64 = C.POINTER(C.c_int64)
+    i32 = C.POINTER(C.c_int32)
+    dp = C.POINTER(C.c_double)
+
+    def deal(nranks, speed):
+        own = np.full(n, -1, dtype=np.int32)
+        sp = None if speed is None else np.asarray(speed, dtype=np.float64)
+        rc = lib.c2b_deal_sources(n, cost.ctypes.data_as(i64), nranks, None if sp is None else sp.ctypes.data_as(dp),
+                                  own.ctypes.data_as(i32))
+        assert rc == 0
+        return own
+
+    own = deal(8, None)
+    assert own.min() == 0 and own.max() == 7
+    share = np.array([cost[own == r].sum() for r in range(8)], dtype=np.float64)
+    assert np.max(np.abs(share / share.mean() - 1)) < 1e-3          # equal speeds: equal cost within one long trace
+    assert np.array_equal(own, deal(8, None))                        # deterministic
+    own2 = deal(2, [2.0, 1.0])
+    s0, s1 = cost[own2 == 0].sum(), cost[own2 == 1].sum()
+    assert s0 / s1 == pytest.approx(2.0, rel=1e-3)                   # twice the speed, twice the work
+    # one rank: everything to rank 0; bad arguments are refused
+    assert np.all(deal(1, None) == 0)
+    assert lib.c2b_deal_sources(n, None, 2, None, own.ctypes.data_as(i32)) != 0
+    assert lib.c2b_deal_sources(0, None, 2, None, None) == 0
