@@ -110,6 +110,7 @@ struct c2b_handle {
   std::vector<int> morton_all;     // all sources in Z-order of their mesh position
   std::vector<double> rank_speed;  // updates per ms of every rank's last ray-trace pass (as dealt with)
   bool balance = false;            // nranks > 1 and not disabled
+  long long redeals = 0;
   int* h_nbox_all = nullptr;       // pinned: nbox of every source after the all-reduce
   std::vector<int> work;      // 0-based source indices of this rank
   std::vector<int> work_morton;  // the same indices in Z-order of their mesh position (L2 locality of concurrent traces)
@@ -1176,43 +1177,55 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaEventElapsedTime(&ms_ar, h->ev[2], h->ev[3]));
     if (h->balance && h->NumSrc > 0) {
-      // Deal the sources again for the next pass when a predicted trace length changed or a rank's measured speed
-      // moved by more than 2 %: the same inputs on every rank (all-reduced), so the same assignment everywhere.
-      bool redeal = false;
+      // Deal the sources again for the next pass when the shares of the predicted work have drifted from the ranks'
+      // measured speeds by more than 1.5 %: the same inputs on every rank (all-reduced), so the same decision and
+      // the same assignment everywhere.
       for (int s2 = 0; s2 < h->NumSrc; ++s2)
         if (h->nbox_pred[(size_t)s2] != h->h_nbox_all[s2]) {
           h->nbox_pred[(size_t)s2] = h->h_nbox_all[s2];
-          redeal = true;
+          if (h->owner[(size_t)s2] == h->cfg.rank) h->routes_valid = false;   // this rank sorts and routes again
         }
-      // relative speeds (mean 1), half-way between the last deal's and this pass's measurement
-      std::vector<double> speed((size_t)nr, 0.0);
+      // relative speeds (mean 1), half-way between the last value and this pass's measurement
       bool have_speed = true;
       double ssum = 0.0;
+      std::vector<double> speed((size_t)nr, 0.0);
       for (int r = 0; r < nr; ++r) {
         const double ms = h->h_small[4 + 2 * r], up = h->h_small[5 + 2 * r];
         if (ms > 0.0 && up > 0.0) speed[(size_t)r] = up / ms;
         else have_speed = false;
         ssum += speed[(size_t)r];
       }
-      if (have_speed) {
-        for (int r = 0; r < nr; ++r) {
-          speed[(size_t)r] = 0.5 * h->rank_speed[(size_t)r] + 0.5 * speed[(size_t)r] * nr / ssum;
-          if (std::fabs(speed[(size_t)r] - h->rank_speed[(size_t)r]) > 0.01) redeal = true;   // > 1 % of a fair share
-        }
+      if (have_speed)
+        for (int r = 0; r < nr; ++r) h->rank_speed[(size_t)r] = 0.5 * h->rank_speed[(size_t)r] + 0.5 * speed[(size_t)r] * nr / ssum;
+      std::vector<int64_t> cost((size_t)h->NumSrc);
+      std::vector<double> load((size_t)nr, 0.0);
+      double total = 0.0, stot = 0.0;
+      for (int s2 = 0; s2 < h->NumSrc; ++s2) {
+        const int nb = h->nbox_pred[(size_t)s2];
+        if ((size_t)nb >= h->updates_of_nbox.size())
+          for (int k = (int)h->updates_of_nbox.size(); k <= nb; ++k) h->updates_of_nbox.push_back(box_updates(h, k));
+        cost[(size_t)s2] = h->updates_of_nbox[(size_t)nb];
+        const double c1 = (double)std::max<int64_t>(cost[(size_t)s2], 1);
+        load[(size_t)h->owner[(size_t)s2]] += c1;
+        total += c1;
+      }
+      for (int r = 0; r < nr; ++r) stot += h->rank_speed[(size_t)r];
+      bool redeal = false;
+      for (int r = 0; r < nr; ++r) {
+        const double target = total * h->rank_speed[(size_t)r] / stot;
+        if (std::fabs(load[(size_t)r] - target) > 0.015 * target) redeal = true;
       }
       if (redeal) {
-        if (have_speed) h->rank_speed = speed;
-        std::vector<int64_t> cost((size_t)h->NumSrc);
-        for (int s2 = 0; s2 < h->NumSrc; ++s2) {
-          const int nb = h->nbox_pred[(size_t)s2];
-          if ((size_t)nb >= h->updates_of_nbox.size())
-            for (int k = (int)h->updates_of_nbox.size(); k <= nb; ++k) h->updates_of_nbox.push_back(box_updates(h, k));
-          cost[(size_t)s2] = h->updates_of_nbox[(size_t)nb];
-        }
         std::vector<int32_t> own((size_t)h->NumSrc);
         c2b_deal_sources(h->NumSrc, cost.data(), nr, h->rank_speed.data(), own.data());
         h->owner.assign(own.begin(), own.end());
         rebuild_work(h);
+        h->redeals += 1;
+        if (h->cfg.rank == 0 && getenv("C2B_DEBUG_BALANCE")) {
+          fprintf(stderr, "c2b: sources dealt again (%lld): speeds", h->redeals);
+          for (int r = 0; r < nr; ++r) fprintf(stderr, " %.4f", h->rank_speed[(size_t)r]);
+          fprintf(stderr, "\n");
+        }
       }
     }
     loss_sum = h->h_small[0]; nbox_sum = h->h_small[1]; upd_sum = h->h_small[2];
