@@ -12,10 +12,10 @@ Workload (N=1): BASELINE.json configs[2] -- synthetic log-normal density 256^3, 
 density peaks, clumping grid on, LLS on, mid-reionization bubble state (mean ionized fraction 0.54: spheres of up to
 25 cells around the sources) -- the largest configuration that fits one GPU step in seconds.  Every step is one
 evolve3D(dt) call from the SAME snapshot (S1), restored on the device before the call, so the time per step is
-stationary; the early-reionization state S0 (xh = 2e-4) is measured beside it (key "S0").  With --gpus N the source
-list grows to N x 10^4 at a constant source density (weak scaling: the mesh grows with the volume, 256/320/400/512 for
-1/2/4/8 GPUs, same bubble radius, so the traces keep their length and every GPU has the same updates to do;
---scaling strong keeps --mesh and --nsrc for the whole job): every GPU holds the full grids
+stationary; the early-reionization state S0 (xh = 2e-4) is measured beside it (key "S0").  With --gpus N the job is
+N periodic copies of that volume in one mesh (weak scaling: 256x256x512, 256x512x512, 512^3 for 2, 4, 8 GPUs; N x 10^4
+sources, the same density, bubbles and fluxes around every copy of a source, so every GPU has exactly the 1-GPU
+updates to do; --scaling strong keeps --mesh and --nsrc for the whole job): every GPU holds the full grids
 and traces its round-robin share (master_slave.F90:85), the partial rate grids are summed with ncclAllReduce
 (evolve.F90:599-602).  After the timed legs the sampled-source rate grid of the cpu_baseline leg is compared with
 the GPU's ("parity_rel_err", must be <= 1e-6).
@@ -79,42 +79,79 @@ def load_peaks():
         return 6650.0, "fallback"
 
 
+def tiling(world):
+    """(tx, ty, tz): how many copies of the base volume along x, y, z for `world` GPUs -- the most even factorisation,
+    larger factors on the slower axes (1,1,2), (1,2,2), (2,2,2) for 2, 4, 8"""
+    f = [1, 1, 1]
+    n, p = world, 2
+    primes = []
+    while n > 1:
+        while n % p == 0:
+            primes.append(p)
+            n //= p
+        p += 1
+    for q in sorted(primes, reverse=True):
+        i = min(range(3), key=lambda k: (f[k], -k))
+        f[i] *= q
+    return tuple(sorted(f))
+
+
 def job_shape(args, world):
-    """(mesh, sources in total, bubble radius) of the job on `world` GPUs.
-    weak scaling: --nsrc sources per GPU at a constant source density -- the mesh grows with the volume,
-    mesh = 16*round(--mesh * world^(1/3) / 16) (256, 320, 400, 512 for 1, 2, 4, 8 GPUs) -- and the same bubble radius,
-    so that the traces keep their length and every GPU has the same number of updates to do;
+    """(mesh, sources in total, bubble radius, tiles) of the job on `world` GPUs; mesh is an int (cubic) or (n1,n2,n3).
+    weak scaling: the --mesh^3 / --nsrc volume repeated `world` times in one periodic mesh (tiles along x, y, z);
     strong scaling: --mesh and --nsrc describe the whole job."""
     if args.scaling == "strong" or world == 1:
-        return args.mesh, args.nsrc if args.scaling == "strong" else args.nsrc * world, args.bubble
-    mesh = int(round(args.mesh * world ** (1.0 / 3.0) / 16.0)) * 16
-    return mesh, args.nsrc * world, args.bubble
+        return args.mesh, args.nsrc, args.bubble, (1, 1, 1)
+    t = tiling(world)
+    return (args.mesh * t[0], args.mesh * t[1], args.mesh * t[2]), args.nsrc * world, args.bubble, t
 
 
-def _build_workload(mesh, nsrc_total, bubble):
+def ncells(mesh):
+    return int(mesh) ** 3 if np.isscalar(mesh) else int(mesh[0]) * int(mesh[1]) * int(mesh[2])
+
+
+def mesh_name(mesh):
+    return "%d^3" % mesh if np.isscalar(mesh) else "%dx%dx%d" % tuple(mesh)
+
+
+def _build_workload(mesh, nsrc_total, bubble, tiles=(1, 1, 1)):
     from c2ray3dm_b200 import synthetic as syn
     zred = 9.0
-    seed = 20240607 if mesh == 256 else (20240608 if mesh == 512 else 20240600 + mesh)
-    nd = syn.lognormal_density(mesh, zred, seed)
-    pos, nf = syn.sources_at_density_peaks(nd, nsrc_total, 1e7)
+    ntile = tiles[0] * tiles[1] * tiles[2]
+    base = mesh if np.isscalar(mesh) else int(mesh[0]) // tiles[0]
+    nsrc = nsrc_total // ntile
+    seed = 20240607 if base == 256 else (20240608 if base == 512 else 20240600 + base)
+    nd = syn.lognormal_density(base, zred, seed)
+    pos, nf = syn.sources_at_density_peaks(nd, nsrc, 1e7)
     radius = bubble * (nf / nf.max()) ** (1.0 / 3.0)
     xh = syn.bubble_state(nd.shape, pos, radius)
-    dr, vol = syn.proper_geometry(mesh, zred)
-    return dict(zred=zred, ndens=nd, srcpos=pos, normflux=nf, xh=xh, dr=dr, vol=vol,
-                clumping=syn.clumping_from_density(nd, zred), coldensh_LLS=syn.lls_coldens(dr[0], zred))
+    dr, vol = syn.proper_geometry(base, zred)
+    clump = syn.clumping_from_density(nd, zred)
+    if ntile > 1:
+        # N periodic copies of the volume; the copies of a source are consecutive in the list, so the static
+        # round-robin of the first pass (master_slave.F90:85) gives every rank one copy of every source
+        reps = (tiles[2], tiles[1], tiles[0])   # arrays are [z][y][x]
+        nd, xh, clump = np.tile(nd, reps), np.tile(xh, reps), np.tile(clump, reps)
+        offs = np.array([(ix * base, iy * base, iz * base) for iz in range(tiles[2]) for iy in range(tiles[1])
+                         for ix in range(tiles[0])], dtype=pos.dtype)
+        pos = (pos[:, None, :] + offs[None, :, :]).reshape(-1, 3)
+        nf = np.repeat(nf, ntile)
+    return dict(zred=zred, ndens=np.ascontiguousarray(nd), srcpos=np.ascontiguousarray(pos), normflux=nf,
+                xh=np.ascontiguousarray(xh), dr=dr, vol=vol, clumping=np.ascontiguousarray(clump),
+                coldensh_LLS=syn.lls_coldens(dr[0], zred))
 
 
-def build_workload(mesh, nsrc_total, bubble):
+def build_workload(mesh, nsrc_total, bubble, tiles=(1, 1, 1)):
     """inputs of configs[2]/[3], deterministic; `bubble` = radius of the brightest source's sphere.
     Under torchrun the local rank 0 builds them once and the other ranks of the node read them from /dev/shm."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1 or not os.path.isdir("/dev/shm"):
-        return _build_workload(mesh, nsrc_total, bubble)
-    tag = "/dev/shm/c2b_workload_%s_%d_%d_%.4f_%s" % (os.environ.get("MASTER_PORT", "0"), mesh, nsrc_total, bubble,
-                                                      os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+        return _build_workload(mesh, nsrc_total, bubble, tiles)
+    tag = "/dev/shm/c2b_workload_%s_%s_%d_%.4f_%s" % (os.environ.get("MASTER_PORT", "0"), mesh_name(mesh).replace("^", "c"),
+                                                      nsrc_total, bubble, os.environ.get("TORCHELASTIC_RUN_ID", "run"))
     keys = ("ndens", "srcpos", "normflux", "xh", "dr", "clumping")
     if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        w = _build_workload(mesh, nsrc_total, bubble)
+        w = _build_workload(mesh, nsrc_total, bubble, tiles)
         for k in keys:
             np.save(tag + "_" + k + ".npy", w[k])
         with open(tag + ".json.tmp", "w") as f:
@@ -196,9 +233,9 @@ def cpu_sample(w, mesh, nsample, threads, keep=False, in_source=False):
     phih = o.phih.copy() if keep else None
     o.global_pass(0.5e6 * YEAR, r.photon_loss_all)
     t2 = time.perf_counter()
-    desc = ("%d of %d sources (every %dth, file order) of the %d^3 workload: 1 pass_all_sources (%.2fs) + "
+    desc = ("%d of %d sources (every %dth, file order) of the %s workload: 1 pass_all_sources (%.2fs) + "
             "1 global_pass (%.2fs), C restatement, %d threads, mode: %s" % (
-                len(sel), ns, stride, mesh, t1 - t0, t2 - t1, threads,
+                len(sel), ns, stride, mesh_name(mesh), t1 - t0, t2 - t1, threads,
                 "omp-in-source (all threads inside one source: 6 axes / 12 planes / 8 octants, evolve_source.F90:141-186)"
                 if in_source else "source-parallel (one source per thread, private rate grids summed: do_grid_static + "
                                   "MPI_ALLREDUCE)"))
@@ -212,8 +249,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    mesh_job, nsrc_total, bubble = job_shape(args, args.gpus)
-    w = build_workload(mesh_job, nsrc_total, bubble)
+    mesh_job, nsrc_total, bubble, tiles = job_shape(args, args.gpus)
+    w = build_workload(mesh_job, nsrc_total, bubble, tiles)
     nsample = args.cpu_sample or max(cores * 4, 64)
     rates, secs, upd = [], [], []
     desc = ""
@@ -242,18 +279,22 @@ def run_reference(args):
 
 def workload_config(args, world=None):
     world = world or args.gpus
-    mesh, total, bubble = job_shape(args, world)
-    return {"workload": "synthetic lognormal density %d^3, %d sources in total (%s) at density peaks, clumping grid "
+    mesh, total, bubble, tiles = job_shape(args, world)
+    weak = world > 1 and args.scaling == "weak"
+    return {"workload": "synthetic lognormal density %s, %d sources in total (%s) at density peaks, clumping grid "
                         "(type 5), LLS type 1, z=9, dt=%g Myr; every step = one evolve3D call from the same "
                         "mid-reionization snapshot S1 (bubbles r<=%.1f cells, mean x=0.54), restored on the "
                         "device before the call (BASELINE configs[%d]%s)" % (
-                            mesh, total, "%d per GPU, constant source density: the mesh grows with the GPU count" % args.nsrc
-                            if args.scaling == "weak" else "strong scaling", args.dt_myr, bubble,
-                            3 if mesh == 512 else 2, "" if world == 1 or args.scaling == "strong" else ", weak-scaled"),
-            "mesh": mesh, "sources_total": total, "parallelism": "source-sharded x%d" % world,
+                            mesh_name(mesh), total,
+                            ("weak scaling: %d periodic copies (%dx%dx%d) of the %d^3 / %d-source volume in one mesh, every "
+                             "GPU has the 1-GPU updates to do" % (world, tiles[0], tiles[1], tiles[2], args.mesh, args.nsrc))
+                            if weak else ("strong scaling" if world > 1 else "one GPU"), args.dt_myr, bubble,
+                            3 if args.mesh == 512 else 2, ", weak-scaled" if weak else ""),
+            "mesh": mesh if np.isscalar(mesh) else list(mesh), "sources_total": total,
+            "parallelism": "source-sharded x%d" % world,
             "state": "S1 restored every step (stationary)",
-            "l2": "grids (tau_cell + twin + phih + twin = %.0f MB) exceed the 126 MB L2" % (32 * mesh ** 3 / 1e6)
-            if mesh >= 256 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
+            "l2": "grids (tau_cell + twin + phih + twin = %.0f MB) exceed the 126 MB L2" % (32 * ncells(mesh) / 1e6)
+            if ncells(mesh) >= 256 ** 3 else "grids fit in L2; L2 flushed between steps by the chemistry pass"}
 
 
 def run_ours(args):
@@ -273,8 +314,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mesh, nsrc_total, bubble = job_shape(args, world)
-    w = build_workload(mesh, nsrc_total, bubble)
+    mesh, nsrc_total, bubble, tiles = job_shape(args, world)
+    w = build_workload(mesh, nsrc_total, bubble, tiles)
+    nc = ncells(mesh)
     dt = args.dt_myr * 1e6 * YEAR
 
     e = Evolve(mesh, device=local, rank=rank, nranks=world, type_of_clumping=5, use_LLS=True, type_of_LLS=1)
@@ -348,8 +390,8 @@ def run_ours(args):
     e2e = None
     dptr = ctypes.POINTER(ctypes.c_double)
     if not args.no_e2e:
-        xh_out = torch.empty(mesh ** 3, dtype=torch.float64).pin_memory()
-        ph_out = torch.empty(mesh ** 3, dtype=torch.float64).pin_memory()
+        xh_out = torch.empty(nc, dtype=torch.float64).pin_memory()
+        ph_out = torch.empty(nc, dtype=torch.float64).pin_memory()
         barrier()
         t0 = time.perf_counter()
         upd2 = 0
@@ -362,8 +404,8 @@ def run_ours(args):
             upd2 += rep.total_updates
         barrier()
         wall2 = maxreduce(time.perf_counter() - t0)
-        e2e = {"value": upd2 / wall2, "unit": UNIT, "h2d_bytes_per_step": 12 * mesh ** 3,
-               "d2h_bytes_per_step": 16 * mesh ** 3, "ms_per_step": 1e3 * wall2 / args.steps}
+        e2e = {"value": upd2 / wall2, "unit": UNIT, "h2d_bytes_per_step": 12 * nc,
+               "d2h_bytes_per_step": 16 * nc, "ms_per_step": 1e3 * wall2 / args.steps}
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
@@ -371,7 +413,7 @@ def run_ours(args):
     s0 = None
     if not args.no_s0:
         from c2ray3dm_b200 import constants as K
-        xh0 = torch.full((mesh ** 3,), K.xh_initial, dtype=torch.float64).pin_memory()
+        xh0 = torch.full((nc,), K.xh_initial, dtype=torch.float64).pin_memory()
         u0 = rt0 = 0.0
         t_s0 = 0.0
         for i in range(3):
@@ -411,7 +453,7 @@ def run_ours(args):
                                       "chemistry": ms_chem / args.steps, "device_total": ms_dev / args.steps},
                 "roofline": {"kernel": "raytrace_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": NCU_DRAM_BYTES_PER_UPDATE * upd_rank / max(1, niter) if mesh == 256 else None,
+                             "traffic": NCU_DRAM_BYTES_PER_UPDATE * upd_rank / max(1, niter) if (args.mesh == 256 and args.bubble == 25.0) else None,
                              "traffic_note": "bytes per launch = %.1f B/update (ncu dram bytes of one launch of this "
                                              "workload, profiles/) x updates per launch" % NCU_DRAM_BYTES_PER_UPDATE,
                              "algorithmic_bytes_per_launch": B_RT * upd_rank / max(1, niter),
