@@ -1178,14 +1178,14 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     CU(h, cudaEventElapsedTime(&ms_ar, h->ev[2], h->ev[3]));
     if (h->balance && h->NumSrc > 0) {
       // Deal the sources again for the next pass when the shares of the predicted work have drifted from the ranks'
-      // measured speeds by more than 1.5 %: the same inputs on every rank (all-reduced), so the same decision and
+      // measured speeds by more than 2.5 %: the same inputs on every rank (all-reduced), so the same decision and
       // the same assignment everywhere.
       for (int s2 = 0; s2 < h->NumSrc; ++s2)
         if (h->nbox_pred[(size_t)s2] != h->h_nbox_all[s2]) {
           h->nbox_pred[(size_t)s2] = h->h_nbox_all[s2];
           if (h->owner[(size_t)s2] == h->cfg.rank) h->routes_valid = false;   // this rank sorts and routes again
         }
-      // relative speeds (mean 1), half-way between the last value and this pass's measurement
+      // relative speeds (mean 1), moved 30 % of the way from the last value to this pass's measurement
       bool have_speed = true;
       double ssum = 0.0;
       std::vector<double> speed((size_t)nr, 0.0);
@@ -1196,7 +1196,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
         ssum += speed[(size_t)r];
       }
       if (have_speed)
-        for (int r = 0; r < nr; ++r) h->rank_speed[(size_t)r] = 0.5 * h->rank_speed[(size_t)r] + 0.5 * speed[(size_t)r] * nr / ssum;
+        for (int r = 0; r < nr; ++r) h->rank_speed[(size_t)r] = 0.7 * h->rank_speed[(size_t)r] + 0.3 * speed[(size_t)r] * nr / ssum;
       std::vector<int64_t> cost((size_t)h->NumSrc);
       std::vector<double> load((size_t)nr, 0.0);
       double total = 0.0, stot = 0.0;
@@ -1213,7 +1213,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       bool redeal = false;
       for (int r = 0; r < nr; ++r) {
         const double target = total * h->rank_speed[(size_t)r] / stot;
-        if (std::fabs(load[(size_t)r] - target) > 0.015 * target) redeal = true;
+        if (std::fabs(load[(size_t)r] - target) > 0.025 * target) redeal = true;
       }
       if (redeal) {
         std::vector<int32_t> own((size_t)h->NumSrc);
