@@ -71,9 +71,16 @@ def test_heating_pass_matches_oracle(case, routing, tables4, monkeypatch):
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "N%s_%s" % (c["N"], c["state"]))
-def test_thermal_evolve3d_matches_oracle(case, tables4):
+@pytest.mark.parametrize("routing", ["auto", "warp"])
+def test_thermal_evolve3d_matches_oracle(case, routing, tables4, monkeypatch):
     """two consecutive evolve3D steps with heating and cooling: iteration counts and convergence counters exact,
-    ionized fractions, the three temperatures, the rates and the photon statistics within tolerance"""
+    ionized fractions, the three temperatures, the rates and the photon statistics within tolerance ("warp": every
+    source whose previous trace ended after one subbox goes to the one-warp-per-source kernel, heating variant)"""
+    if routing == "warp":
+        monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
+        monkeypatch.setenv("C2B_WARP_MIN_SOURCES", "1")
+    else:
+        monkeypatch.delenv("C2B_WARP_MIN_SOURCES", raising=False)
     p = make_problem(**case)
     if case["state"] == "random":
         p["xh"] = 1 - (1 - p["xh"]) * 1e-2
