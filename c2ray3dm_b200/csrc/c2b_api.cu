@@ -87,6 +87,7 @@ struct c2b_handle {
   unsigned int* h_ovf = nullptr;   // pinned: number of handed-over sources of the last pass
   // the three work lists of the last pass: they stay on the device while no source's predicted length changes
   bool routes_valid = false;
+  double est_updates = 0.0;     // predicted updates of the CTA + cluster kernels for the cached routes
   int n_small = 0, n_large = 0, n_tiny = 0;
   std::vector<int64_t> updates_of_nbox;   // cells of the final subbox for nbox = 0, 1, 2, ...
   long long route_counts[4] = {0, 0, 0, 0};
@@ -886,8 +887,10 @@ static void absorb_after(c2b_handle* h, double dt) {
 // novf > 0: follow-up call after a pass in which only the per-warp kernel ran and handed `novf` sources over (they are
 // in d_ovf, their number in d_ticket[3]): the single-CTA kernel traces just those.
 // The launches are bracketed by the events ev[e0], ev[e0+1]; the caller reads the time after its own synchronisation.
+// est_updates: predicted updates of the CTA / cluster kernels in this call (decides whether the twin grids pay).
 static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int* d_work_cl, int nwork_cl,
-                         const int* d_work_w, int nwork_w, int novf, double* coldens_dbg, int e0) {
+                         const int* d_work_w, int nwork_w, int novf, double* coldens_dbg, int e0,
+                         double est_updates = 1e300) {
   const c2b_config& c = h->cfg;
   RtParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -964,7 +967,14 @@ static int trace_sources(c2b_handle* h, const int* d_work, int nwork, const int*
   // the single-CTA and the cluster kernel work on the y-fastest twins for their x-principal faces; the per-warp
   // kernel does not, so a pass it handles alone needs neither the transposes nor the twin of the rate grid
   const bool run_cta = nwork > 0 || novf > 0;
-  const bool need_twins = run_cta || nwork_cl > 0;
+  // The twins cost three grid-sized passes per call (transpose of tau_cell, clear and fold-back of the rate twin:
+  // ~48 B per cell); without them the x-principal faces (a third of the updates) touch a 32-byte sector per 8-byte
+  // value (~48 B per such update more).  So the twins pay from about 3 updates per mesh cell on -- always with
+  // thousands of sources, never for the single-source and ten-source configurations.
+  bool use_twins = est_updates >= 3.0 * (double)h->ncell;
+  if (const char* env = getenv("C2B_TWINS")) use_twins = atoi(env) != 0;   // development / tests: force either way
+  rp.use_twins = use_twins ? 1 : 0;
+  const bool need_twins = use_twins && (run_cta || nwork_cl > 0);
   if (need_twins && h->taucell_t_dirty) {
     launch_to_yfast(h->d_taucell, h->d_taucell_t, c.mesh, h->stream);
     h->launches += 1;
@@ -1115,10 +1125,19 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     if (!large.empty())
       CU(h, cudaMemcpyAsync(h->d_work2, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     h->n_small = (int)small.size(); h->n_large = (int)large.size(); h->n_tiny = (int)tiny.size();
+    // predicted updates of the CTA and cluster kernels (a source never traced before counts as a full box)
+    h->est_updates = 0.0;
+    for (const std::vector<int>* v : {&small, &large})
+      for (int w : *v) {
+        const int nb = h->nbox_pred[w];
+        if ((size_t)nb >= h->updates_of_nbox.size())
+          for (int k = (int)h->updates_of_nbox.size(); k <= nb; ++k) h->updates_of_nbox.push_back(box_updates(h, k));
+        h->est_updates += nb > 0 ? (double)h->updates_of_nbox[(size_t)nb] : (double)h->ncell;
+      }
     h->routes_valid = true;
     }
     const int n_small = h->n_small, n_large = h->n_large, n_tiny = h->n_tiny;
-    if (int rc = trace_sources(h, h->d_work, n_small, h->d_work2, n_large, h->d_work3, n_tiny, 0, nullptr, 0)) return rc;
+    if (int rc = trace_sources(h, h->d_work, n_small, h->d_work2, n_large, h->d_work3, n_tiny, 0, nullptr, 0, h->est_updates)) return rc;
     CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->h_ovf, h->d_ticket + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
@@ -1127,7 +1146,8 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     if (n_small == 0 && n_tiny > 0 && *h->h_ovf > 0u) {
       // only the per-warp kernel ran and some of its sources need more than one subbox: the single-CTA kernel
       // carries on with those (when the single-CTA kernel runs in the same pass it takes them there and then)
-      if (int rc = trace_sources(h, nullptr, 0, nullptr, 0, nullptr, 0, (int)*h->h_ovf, nullptr, 4)) return rc;
+      if (int rc = trace_sources(h, nullptr, 0, nullptr, 0, nullptr, 0, (int)*h->h_ovf, nullptr, 4,
+                                 (double)*h->h_ovf * (double)box_updates(h, 2))) return rc;
       CU(h, cudaMemcpyAsync(h->h_nbox, h->d_nbox, (size_t)h->NumSrc * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CU(h, cudaMemcpyAsync(h->h_loss, h->d_loss, (size_t)h->NumSrc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CU(h, cudaStreamSynchronize(h->stream));

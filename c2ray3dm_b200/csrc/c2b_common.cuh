@@ -62,6 +62,7 @@ struct RtParams {
   double vol_cell;          // dr(1)*dr(2)*dr(3), vol_ph of the source cell (:153)
   int use_lls, type_lls;
   int cubic_cells;          // dr(1)==dr(2)==dr(3)
+  int use_twins;            // the x-principal faces of the CTA / cluster kernels work on the y-fastest twins (else: strided, on the x-fastest grids)
   double tau_lls;           // sigma_HI*coldensh_LLS
   double rmax_lls2;
   double sigma_HI, inv_sigma, inv_sigma_dr0, fourpi_over_sigma;

@@ -596,7 +596,11 @@ __global__ void __launch_bounds__(kT, kCtaPerSm) raytrace_kernel(RtParams P) {
       lr1 = min(reach, P.lim[1][1]); ll1 = min(reach, P.lim[1][0]);
       lr2 = min(reach, P.lim[2][1]); ll2 = min(reach, P.lim[2][0]);
       const int rmax = max(max(max(lr0, ll0), max(lr1, ll1)), max(lr2, ll2));
-      if (tid < kNf) s_face[tid] = make_face<true>(P, (int)crank * kNf + tid, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2);
+      if (tid < kNf) {
+        const int f = (int)crank * kNf + tid;
+        s_face[tid] = P.use_twins ? make_face<true>(P, f, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2)
+                                  : make_face<false>(P, f, src0, src1, src2, lr0, ll0, lr1, ll1, lr2, ll2);
+      }
       double loss = 0.0;
       if (r_done < 0) {
         // shell 0 = the source cell (evolve_point.F90:151-160): coldensh_in=0, path=dr/2, vol_ph=cell volume.

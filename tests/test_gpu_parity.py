@@ -26,6 +26,12 @@ def routing(request, monkeypatch):
     one-CTA-per-source kernel only, with the cluster-of-6 kernel only, and with the one-warp-per-source kernel
     taking every source whose previous trace ended after one subbox (the rest: one CTA per source)"""
     monkeypatch.delenv("C2B_WARP_MIN_SOURCES", raising=False)
+    # the y-fastest twin grids of the x-principal faces: forced on with "cta", off with "cluster", by size otherwise
+    monkeypatch.delenv("C2B_TWINS", raising=False)
+    if request.param == "cta":
+        monkeypatch.setenv("C2B_TWINS", "1")
+    elif request.param == "cluster":
+        monkeypatch.setenv("C2B_TWINS", "0")
     if request.param == "warp":
         monkeypatch.setenv("C2B_CLUSTER_MIN_NBOX", "100000")
         monkeypatch.setenv("C2B_DEBUG_CLUSTER", "0")
