@@ -41,13 +41,13 @@ UNIT = "updates/s"
 B_RT = 28.0  # algorithmic HBM bytes per ray-trace update: ndens 4 + xh_av 8 + phih RMW 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one raytrace_kernel launch on this workload divided by
 # the updates of that launch (ncu --set full capture, profiles/ncu_raytrace_r2_summary.txt)
-NCU_DRAM_BYTES_PER_UPDATE = 20.3
+NCU_DRAM_BYTES_PER_UPDATE = 20.4
 # the same capture (profiles/ncu_raytrace_r2_summary.txt): measured counters, not static instruction counts
 NCU_SOURCE = "profiles/ncu_raytrace_r2_summary.txt"
 NCU_DRAM_PCT = 35.8         # gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
-NCU_FP64_PCT = 45.8         # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
+NCU_FP64_PCT = 45.5         # sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
 NCU_ISSUE_PCT = 54.3        # smsp__issue_active.avg.pct_of_peak_sustained_active
-NCU_INSTR_PER_UPDATE = 4.35 # smsp__inst_executed.sum / updates of the launch
+NCU_INSTR_PER_UPDATE = 4.39 # smsp__inst_executed.sum / updates of the launch
 YEAR = 3.15576e7
 
 
