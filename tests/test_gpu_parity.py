@@ -566,3 +566,30 @@ def test_warp_per_source_kernel_and_hand_over(lls, clump, gpu_tables, monkeypatc
     nb = e.source_nbox()
     assert nb[5] == 0 and nb.max() >= 2
     e.close()
+
+
+@pytest.mark.parametrize("subboxsize", [2, 3, 8])
+def test_warp_kernel_other_subbox_sizes(subboxsize, gpu_tables, monkeypatch, routing):
+    """the oracle carries the reference's subboxsize = 5 (c2ray_parameters.f90:54); for other sizes the
+    one-warp-per-source kernel (planes sized from subboxsize, hand-over after the first subbox) must reproduce the
+    one-CTA kernel: subbox counts and update counts exactly, rates to rounding (the additions are in another order)"""
+    if routing != "warp":
+        pytest.skip("runs once, with the warp routing")
+    p = make_problem(36, nsrc=60, seed=41, state="neutral", use_LLS=True, flux=2e6)
+    p["normflux"][::5] *= 3000.0
+    res = []
+    for use_warp in (True, False):
+        monkeypatch.setenv("C2B_NO_WARP_KERNEL", "0" if use_warp else "1")
+        e = setup_gpu(p, tables=gpu_tables, subboxsize=subboxsize)
+        for step in range(2):
+            rep = e.evolve3D(step * DT, DT)
+        res.append((rep.niter, rep.total_updates, list(rep.sum_nbox_all[1:rep.niter + 1]), e.source_nbox().copy(),
+                    e.phih_grid.copy(), e.xh.copy(), e.route_counts()))
+        e.close()
+    (n1, u1, s1, nb1, ph1, x1, rc1), (n2, u2, s2, nb2, ph2, x2, rc2) = res
+    assert rc1[2] > 0 and rc2[2] == 0                       # the warp kernel ran in the first run only
+    assert (n1, u1, s1) == (n2, u2, s2) and np.array_equal(nb1, nb2)
+    assert np.array_equal(ph1 != 0, ph2 != 0)
+    nz = ph2 != 0
+    assert np.max(np.abs(ph1[nz] - ph2[nz]) / ph2[nz]) < 1e-8   # second step: the order of the additions feeds back
+    np.testing.assert_allclose(x1, x2, rtol=0, atol=1e-10)
