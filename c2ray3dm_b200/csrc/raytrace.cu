@@ -70,7 +70,6 @@ constexpr int kT = C2B_RT_THREADS; // threads per CTA
 constexpr int kFaces = 6;
 constexpr int kClusterSize = 6;    // the many-CTA work group: one CTA per face
 constexpr int kCtaPerSm = C2B_CTA_PER_SM;
-constexpr int kWarps = kT / 32;
 #ifndef C2B_RT_ILP
 #define C2B_RT_ILP 4
 #endif
