@@ -745,7 +745,7 @@ int c2b_set_cooling_table(c2b_handle* h, const double* log10_temp, const double*
   C2B_CHECK_H(h);
   if (int rc = need_thermal(h, "c2b_set_cooling_table")) return rc;
   if (!log10_temp || !log10_cool) return fail(h, "c2b_set_cooling_table: null pointer");
-  if (n != 61) return fail(h, "c2b_set_cooling_table: the CIE table has 61 rows (cooling.f90:29)");
+  if (n != 61) return fail(h, "c2b_set_cooling_table: the CIE table has 61 rows (cooling.f90:26)");
   if (bind_device(h)) return 1;
   double cie[64] = {0};
   for (int i = 0; i < 61; ++i) cie[i] = std::pow(10.0, log10_cool[i]);   // cooling.f90:84-86

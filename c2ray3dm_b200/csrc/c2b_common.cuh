@@ -127,7 +127,7 @@ struct ChemParams {
   float* T_avg;            // %average: in = previous iterate, out = new time average
   float* T_int;            // %intermed: out
   const double* phiheat;   // evolve_data.F90:42
-  const double* cie_cool;  // 61 entries, cooling.f90:29
+  const double* cie_cool;  // 61 entries, cooling.f90:26-27
   double cool_mintemp, cool_dtemp;
   double k_B, gamma1, minitemp, relative_denergy;
   double cosmo_cool_factor;   // 2/(1+zred)*dzdt (cosmology.F90:198-225), 0 when not cosmological

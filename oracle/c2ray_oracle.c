@@ -325,7 +325,7 @@ struct orc_state {
   double heat_thick[ORC_NUMTAU + 1], heat_thin[ORC_NUMTAU + 1]; /* stellar_heat_*_table(:,1) */
   double *phiheat_grid;               /* evolve_data.F90:42 */
   float *temperature_grid;            /* temperature_module.F90:21-35: (current, average, intermed) per cell */
-  double cie_cool[61], cool_mintemp, cool_dtemp; /* cooling.f90:29-32 */
+  double cie_cool[61], cool_mintemp, cool_dtemp; /* cooling.f90:26-29 */
   /* iteration dump (evolve.F90:285-324) kept in memory */
   int dump_at_iter, have_dump, dump_niter;
   double dump_photon_loss_all;
