@@ -1198,7 +1198,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
     CU(h, cudaEventElapsedTime(&ms_ar, h->ev[2], h->ev[3]));
     if (h->balance && h->NumSrc > 0) {
       // Deal the sources again for the next pass when the shares of the predicted work have drifted from the ranks'
-      // measured speeds by more than 2.5 %: the same inputs on every rank (all-reduced), so the same decision and
+      // measured speeds by more than 1.5 %: the same inputs on every rank (all-reduced), so the same decision and
       // the same assignment everywhere.
       for (int s2 = 0; s2 < h->NumSrc; ++s2)
         if (h->nbox_pred[(size_t)s2] != h->h_nbox_all[s2]) {
@@ -1233,7 +1233,7 @@ int c2b_pass_all_sources(c2b_handle* h, int32_t niter, double dt, c2b_pass_repor
       bool redeal = false;
       for (int r = 0; r < nr; ++r) {
         const double target = total * h->rank_speed[(size_t)r] / stot;
-        if (std::fabs(load[(size_t)r] - target) > 0.025 * target) redeal = true;
+        if (std::fabs(load[(size_t)r] - target) > 0.015 * target) redeal = true;
       }
       if (redeal) {
         std::vector<int32_t> own((size_t)h->NumSrc);
