@@ -157,6 +157,7 @@ def build_workload(mesh, nsrc_total, bubble, tiles=(1, 1, 1)):
         with open(tag + ".json.tmp", "w") as f:
             json.dump({"zred": w["zred"], "vol": w["vol"], "coldensh_LLS": w["coldensh_LLS"]}, f)
         os.rename(tag + ".json.tmp", tag + ".json")
+        w["_shm_tag"] = tag
         return w
     t0 = time.time()
     while not os.path.exists(tag + ".json"):
@@ -503,6 +504,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if w.get("_shm_tag"):   # the local rank 0 removes the workload files it shared through /dev/shm
+        import glob
+        for f in glob.glob(w["_shm_tag"] + "*"):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
     return 0
 
 
