@@ -171,6 +171,17 @@ def build_workload(mesh, nsrc_total, bubble, tiles=(1, 1, 1)):
     return w
 
 
+def remove_shared_workload(w):
+    """the local rank 0 removes the workload files it shared through /dev/shm"""
+    if w.get("_shm_tag"):
+        import glob
+        for f in glob.glob(w["_shm_tag"] + "*"):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+
+
 class ClockSampler(threading.Thread):
     """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
 
@@ -275,6 +286,7 @@ def run_reference(args):
             "note": "reference is Fortran and cannot be built in this image (no Fortran compiler): this is the C "
                     "restatement in oracle/ on the host cores"}
     print(json.dumps(line))
+    remove_shared_workload(w)
     return 0
 
 
@@ -504,13 +516,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if w.get("_shm_tag"):   # the local rank 0 removes the workload files it shared through /dev/shm
-        import glob
-        for f in glob.glob(w["_shm_tag"] + "*"):
-            try:
-                os.remove(f)
-            except OSError:
-                pass
+    remove_shared_workload(w)
     return 0
 
 
