@@ -256,12 +256,24 @@ def cpu_sample(w, mesh, nsample, threads, keep=False, in_source=False):
     return r.updates / (t1 - t0), desc, t2 - t0, r.updates
 
 
+def cpu_threads(mesh):
+    """host threads for the CPU restatement: all cores, unless their private grids (column density + rate grid per
+    thread, 16 B per cell) would take more than a quarter of the host memory or 64 GB"""
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        budget = min(0.25 * psutil.virtual_memory().total, 64e9)
+    except Exception:
+        budget = 16e9
+    return max(1, min(cores, int(budget / (16.0 * ncells(mesh)))))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
     mesh_job, nsrc_total, bubble, tiles = job_shape(args, args.gpus)
+    cores = cpu_threads(mesh_job)
     w = build_workload(mesh_job, nsrc_total, bubble, tiles)
     nsample = args.cpu_sample or max(cores * 4, 64)
     rates, secs, upd = [], [], []
@@ -481,7 +493,7 @@ def run_ours(args):
                 "S0": s0,
                 "e2e": e2e}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads(mesh)
         nsample = args.cpu_sample or max(cores * 4, 64)
         v, desc, s, u, sel, ph_cpu = cpu_sample(w, mesh, nsample, cores, keep=True)
         if s < 5:  # scale the sample towards ~10-30 s of CPU work
