@@ -22,7 +22,9 @@
 // (the device-side do_grid_master, master_slave.F90:124-231).  A work group is one CTA of 256
 // threads (two resident per SM) or, when there are too few long traces to fill the GPU that way, a
 // thread-block cluster of 6 CTAs, one per cube face, whose boundary-loss partial sums meet in rank
-// 0's shared memory over DSMEM once per subbox pass.  Within a shell a thread owns a column (face,
+// 0's shared memory over DSMEM once per subbox pass, or -- for the first subbox of the many short
+// traces of early reionization -- a single warp (raytrace_warp_kernel below; what outgrows the
+// first subbox is handed over to the one-CTA shape on the device).  Within a shell a thread owns a column (face,
 // transverse index a), or a b-segment of it, and walks b, updating the FOUR quadrants of its face
 // together: the interpolation weights, the path length and the dilution volume depend only on
 // (r,a,b), so they are computed once per four cells, and the four dependency chains interleave in
@@ -32,7 +34,7 @@
 // while they fit, afterwards in a per-CTA global scratch.  The optical-depth table is staged in
 // shared memory as (value, forward difference) pairs.  Faces whose principal axis is x walk planes
 // of constant x; they read and accumulate into y-fastest twins of the grids so that their accesses
-// are contiguous too.
+// are contiguous too (when the pass has enough work to pay for the transposes: RtParams::use_twins).
 //
 // Upstream cells that do not exist in plane r-1 (a-1 < 0, b-1 < 0, a == r, b == r) are read as
 // whatever finite value the buffer holds: their bilinear weight is exactly 0 (the weights are built
