@@ -312,6 +312,29 @@ module c2ray_b200_iface
        type(c_ptr),value :: tg
      end function c2b_set_iter_state_thermal
 
+     !> per-source subbox counts of the last pass (with npr > 1: of every source, all-reduced), for the MPILOG
+     !! diagnostics of do_source (evolve_source.F90:216-219)
+     integer(c_int) function c2b_get_source_nbox(handle,nbox) bind(C,name="c2b_get_source_nbox")
+       import
+       type(c_ptr),value :: handle
+       integer(c_int32_t),intent(out) :: nbox(*)
+     end function c2b_get_source_nbox
+
+     !> which rank traces which source in the next pass (0-based ranks; the library's counterpart of
+     !! do_grid_master, master_slave.F90:124-231)
+     integer(c_int) function c2b_get_source_owner(handle,owner) bind(C,name="c2b_get_source_owner")
+       import
+       type(c_ptr),value :: handle
+       integer(c_int32_t),intent(out) :: owner(*)
+     end function c2b_get_source_owner
+
+     !> sources dealt so far to the work-group shapes: one CTA, one cluster, one warp, handed over by the warp shape
+     integer(c_int) function c2b_get_route_counts(handle,counts) bind(C,name="c2b_get_route_counts")
+       import
+       type(c_ptr),value :: handle
+       integer(c_int64_t),intent(out) :: counts(4)
+     end function c2b_get_route_counts
+
   end interface
 
 contains
