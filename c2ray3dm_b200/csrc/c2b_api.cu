@@ -542,6 +542,29 @@ int c2b_set_clumping_grid(c2b_handle* h, const float* g) {
   return upload_f32_grid(h, &h->d_clump, g);
 }
 
+int c2b_set_clumping_from_density(c2b_handle* h, double p1, double p2, double p3, double avg_dens) {
+  C2B_CHECK_H(h);
+  if (h->cfg.type_of_clumping < 3) return fail(h, "c2b_set_clumping_from_density: type_of_clumping is 1 or 2 (scalar)");
+  if (!h->have_density) return fail(h, "c2b_set_clumping_from_density: density not set (c2b_set_density)");
+  if (!(avg_dens > 0.0)) return fail(h, "c2b_set_clumping_from_density: avg_dens must be positive");
+  if (bind_device(h)) return 1;
+  if (!h->d_clump) CU(h, cudaMalloc(&h->d_clump, h->ncell * sizeof(float)));
+  launch_clumping_from_density(h->d_ndens, h->d_clump, h->ncell, p1, p2, p3, avg_dens, h->stream);
+  h->launches += 1;
+  CU(h, cudaGetLastError());
+  return 0;
+}
+
+int c2b_get_clumping_grid(c2b_handle* h, float* g) {
+  C2B_CHECK_H(h);
+  if (!g) return fail(h, "c2b_get_clumping_grid: null pointer");
+  if (!h->d_clump) return fail(h, "c2b_get_clumping_grid: no clumping grid on the device");
+  if (bind_device(h)) return 1;
+  CU(h, cudaMemcpyAsync(g, h->d_clump, h->ncell * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int c2b_set_lls_scalar(c2b_handle* h, double v) {
   C2B_CHECK_H(h);
   h->coldensh_LLS = v;

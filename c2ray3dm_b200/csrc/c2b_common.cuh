@@ -143,6 +143,8 @@ void launch_stats(const ChemParams& p, const double* x_l, const double* x_r, int
 void launch_unpack_temperature(const float* aos, float* cur, float* avg, float* inter, size_t n, cudaStream_t stream);
 void launch_pack_temperature(const float* cur, const float* avg, const float* inter, float* aos, size_t n, cudaStream_t stream);
 void launch_fill_f32(float* a, float v, size_t n, cudaStream_t stream);
+void launch_clumping_from_density(const float* ndens, float* clump, size_t n, double p1, double p2, double p3,
+                                  double avg_dens, cudaStream_t stream);
 void launch_finalize_partials(const double* partials, int nblocks, double* out /*kNumStat*/,
                               cudaStream_t stream);
 void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream);

@@ -327,6 +327,17 @@ __global__ void scale_density_kernel(float* ndens, size_t n, double zfactor3) {
     ndens[c] = (float)((double)ndens[c] / zfactor3);
 }
 
+// deterministic_clumping, clumping_module.F90:327-363: clumping_grid = real(p1*d*d + p2*d + p3), d = ndens/avg_dens,
+// evaluated left to right in double as the Fortran expression (:356-357) and rounded to default real
+__global__ void clumping_from_density_kernel(const float* __restrict__ ndens, float* __restrict__ clump, size_t n,
+                                             double p1, double p2, double p3, double avg_dens) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    const double nd = (double)ndens[c];
+    clump[c] = (float)(p1 * nd / avg_dens * nd / avg_dens + p2 * nd / avg_dens + p3);
+  }
+}
+
 __global__ void unpack_temperature_kernel(const float* __restrict__ aos, float* cur, float* avg, float* inter, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
@@ -420,6 +431,10 @@ void launch_finalize_partials(const double* partials, int nblocks, double* out, 
 }
 void launch_scale_density(float* ndens, size_t n, double zfactor3, cudaStream_t stream) {
   scale_density_kernel<<<chemistry_blocks(), 256, 0, stream>>>(ndens, n, zfactor3);
+}
+void launch_clumping_from_density(const float* ndens, float* clump, size_t n, double p1, double p2, double p3,
+                                  double avg_dens, cudaStream_t stream) {
+  clumping_from_density_kernel<<<chemistry_blocks(), 256, 0, stream>>>(ndens, clump, n, p1, p2, p3, avg_dens);
 }
 void launch_unpack_temperature(const float* aos, float* cur, float* avg, float* inter, size_t n, cudaStream_t stream) {
   unpack_temperature_kernel<<<chemistry_blocks(), 256, 0, stream>>>(aos, cur, avg, inter, n);

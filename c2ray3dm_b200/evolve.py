@@ -295,6 +295,17 @@ class Evolve:
         self._ck(self.L.c2b_measure_dfma_rate(self.h, C.byref(r)), "c2b_measure_dfma_rate")
         return r.value
 
+    def set_clumping_from_density(self, p1, p2, p3, avg_dens):
+        """deterministic_clumping (clumping_module.F90:327-363) on the device-resident density"""
+        self._ck(self.L.c2b_set_clumping_from_density(self.h, float(p1), float(p2), float(p3), float(avg_dens)),
+                 "c2b_set_clumping_from_density")
+
+    @property
+    def clumping_grid(self):
+        out = np.empty(self.ncell, dtype=np.float32)
+        self._ck(self.L.c2b_get_clumping_grid(self.h, _fp(out)), "c2b_get_clumping_grid")
+        return out.reshape(self.shape)
+
     def source_owner(self):
         """rank that traces each source in the next pass (multi-rank load balance)"""
         a = np.zeros(max(1, self.NumSrc), dtype=np.int32)

@@ -73,6 +73,7 @@ c2b_begin_step c2b_pass_all_sources c2b_global_pass c2b_end_step c2b_get_xh c2b_
 c2b_get_xh_intermed c2b_get_phih c2b_get_phih_f32 c2b_get_source_nbox c2b_get_source_loss
 c2b_get_iter_state c2b_set_iter_state c2b_dev_ptr c2b_synchronize c2b_trace_source_debug
 c2b_measure_dfma_rate c2b_save_xh_dev c2b_restore_xh_dev c2b_get_route_counts c2b_deal_sources c2b_get_source_owner
+c2b_set_clumping_from_density c2b_get_clumping_grid
 c2b_set_heat_tables c2b_get_heat_tables c2b_set_cooling_table c2b_set_redshift c2b_set_temperature_grid
 c2b_get_temperature_grid c2b_get_phiheat c2b_get_iter_state_thermal c2b_set_iter_state_thermal""".split()
 
@@ -144,6 +145,8 @@ def load():
     L.c2b_get_route_counts.argtypes = [vp, C.POINTER(C.c_int64)]
     L.c2b_deal_sources.argtypes = [C.c_int32, C.POINTER(C.c_int64), C.c_int32, dp, ip]
     L.c2b_get_source_owner.argtypes = [vp, ip]
+    L.c2b_set_clumping_from_density.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.c2b_get_clumping_grid.argtypes = [vp, fp]
     _lib = L
     return L
 

@@ -147,6 +147,13 @@ int c2b_set_geometry(c2b_handle *h, const double dr[3], double vol);    /* grid.
 int c2b_cosmo_evol(c2b_handle *h, double zfactor);                      /* cosmology.F90:161-193 on the device copy */
 int c2b_set_clumping_scalar(c2b_handle *h, float clumping);             /* clumping_module.F90:17 */
 int c2b_set_clumping_grid(c2b_handle *h, const float *clumping_grid);   /* :18 */
+/* deterministic_clumping (clumping_module.F90:327-363, type_of_clumping 3) on the device-resident density:
+ * clumping_grid = real(p1*d*d + p2*d + p3) with d = ndens/avg_dens; p1..p3 are the redshift-weighted rows of
+ * params_dcm (:350), which the host keeps interpolating (weight_function, :271-307).  Saves the upload of the grid
+ * with every slice.  The stochastic model (type 4, :366-438) draws from random_number after random_seed() per cell
+ * and is not reproducible by construction: the host keeps generating it and passes it with c2b_set_clumping_grid. */
+int c2b_set_clumping_from_density(c2b_handle *h, double p1, double p2, double p3, double avg_dens);
+int c2b_get_clumping_grid(c2b_handle *h, float *clumping_grid);
 int c2b_set_lls_scalar(c2b_handle *h, double coldensh_LLS);             /* LLS.F90:79 */
 int c2b_set_lls_grid(c2b_handle *h, const float *LLS_grid);             /* LLS.F90:81 */
 int c2b_set_lls_rmax(c2b_handle *h, double R_max_LLS);                  /* LLS.F90:107 */

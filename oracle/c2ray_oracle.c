@@ -384,6 +384,17 @@ void orc_set_clumping(orc_state *s, int type, float clumping, const float *grid)
     memcpy(s->clumping_grid, grid, s->ncell * sizeof(float));
   }
 }
+/* deterministic_clumping, clumping_module.F90:327-363 (type_of_clumping 3): the quadratic fit in ndens/avg_dens,
+ * evaluated left to right in real(dp) (:356-357) and stored as default real */
+void orc_deterministic_clumping(orc_state *s, double p1, double p2, double p3, double avg_dens) {
+  s->type_of_clumping = 3;
+  if (!s->clumping_grid) s->clumping_grid = (float *)malloc(s->ncell * sizeof(float));
+  for (size_t c = 0; c < s->ncell; ++c) {
+    const double nd = (double)s->ndens[c];
+    s->clumping_grid[c] = (float)(p1 * nd / avg_dens * nd / avg_dens + p2 * nd / avg_dens + p3);
+  }
+}
+const float *orc_clumping_grid(const orc_state *s) { return s->clumping_grid; }
 void orc_set_lls(orc_state *s, int use_LLS, int type_of_LLS, double coldensh_LLS, const float *grid,
                  double R_max_LLS) {
   s->use_LLS = use_LLS;

@@ -53,6 +53,8 @@ void orc_set_tables(orc_state *s, const double *thick, const double *thin);
 void orc_set_density(orc_state *s, const float *ndens);
 void orc_set_geometry(orc_state *s, const double dr[3], double vol);
 void orc_set_clumping(orc_state *s, int type_of_clumping, float clumping, const float *grid);
+void orc_deterministic_clumping(orc_state *s, double p1, double p2, double p3, double avg_dens);
+const float *orc_clumping_grid(const orc_state *s);
 void orc_set_lls(orc_state *s, int use_LLS, int type_of_LLS, double coldensh_LLS,
                  const float *grid, double R_max_LLS);
 void orc_set_temperature(orc_state *s, double temper_val);

@@ -97,6 +97,9 @@ def lib():
         L.orc_set_density.argtypes = [vp, fp]
         L.orc_set_geometry.argtypes = [vp, dp, C.c_double]
         L.orc_set_clumping.argtypes = [vp, C.c_int, C.c_float, fp]
+        L.orc_deterministic_clumping.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_clumping_grid.argtypes = [vp]
+        L.orc_clumping_grid.restype = fp
         L.orc_set_lls.argtypes = [vp, C.c_int, C.c_int, C.c_double, fp, C.c_double]
         L.orc_set_temperature.argtypes = [vp, C.c_double]
         L.orc_set_sources.argtypes = [vp, C.c_int, ip, dp, C.c_double]
@@ -219,6 +222,14 @@ class Oracle:
         if grid is not None:
             g = np.ascontiguousarray(grid, dtype=np.float32).reshape(-1)
         self.L.orc_set_clumping(self.h, int(type_of_clumping), float(clumping), _fp(g) if g is not None else None)
+
+    def deterministic_clumping(self, p1, p2, p3, avg_dens):
+        """deterministic_clumping (clumping_module.F90:327-363) from the density the oracle holds"""
+        self.L.orc_deterministic_clumping(self.h, float(p1), float(p2), float(p3), float(avg_dens))
+
+    @property
+    def clumping_grid(self):
+        return self._grid("orc_clumping_grid")
 
     def set_lls(self, use_LLS=False, type_of_LLS=1, coldensh_LLS=0.0, grid=None, R_max_LLS=0.0):
         g = None

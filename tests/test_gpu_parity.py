@@ -593,3 +593,27 @@ def test_warp_kernel_other_subbox_sizes(subboxsize, gpu_tables, monkeypatch, rou
     nz = ph2 != 0
     assert np.max(np.abs(ph1[nz] - ph2[nz]) / ph2[nz]) < 1e-8   # second step: the order of the additions feeds back
     np.testing.assert_allclose(x1, x2, rtol=0, atol=1e-10)
+
+
+def test_deterministic_clumping_on_device(gpu_tables, routing):
+    """type_of_clumping 3 generated on the device from the resident density (clumping_module.F90:327-363): the grid
+    is bit-identical to the restatement's, and a pass + per-cell pass with it matches the oracle"""
+    if routing != "auto":
+        pytest.skip("runs once")
+    p = make_problem(24, nsrc=4, seed=19, state="random", use_LLS=True, clumping="grid")
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    p["type_of_clumping"] = 3
+    coef = (0.0319, 1.2041, 2.7519)
+    avg = float(np.mean(p["ndens"], dtype=np.float64))
+    o = setup_oracle(p, tables=gpu_tables)
+    o.deterministic_clumping(*coef, avg)
+    e = setup_gpu(p, tables=gpu_tables)
+    e.set_clumping_from_density(*coef, avg)
+    assert np.array_equal(e.clumping_grid, o.clumping_grid)
+    assert not np.array_equal(e.clumping_grid, p["clumping_grid"])
+    ro = o.evolve3D(DT)
+    rg = e.evolve3D(0.0, DT)
+    assert rg.niter == ro.niter and rg.total_updates == ro.total_updates
+    np.testing.assert_allclose(e.xh, o.xh, rtol=0, atol=X_ATOL)
+    assert rg.final_stats.totrec == pytest.approx(ro.final_stats.totrec, rel=1e-6)
+    e.close()

@@ -396,3 +396,19 @@ def test_omp_in_source_mode_is_exact():
     assert (ra.updates, ra.sum_nbox_all) == (rb.updates, rb.sum_nbox_all)
     assert np.array_equal(a.phih, b.phih)
     assert rb.photon_loss_all == pytest.approx(ra.photon_loss_all, rel=1e-12)
+
+
+def test_deterministic_clumping_model():
+    """deterministic_clumping (clumping_module.F90:327-363): the quadratic fit in ndens/avg_dens, formed in double in
+    the Fortran order of operations and stored as default real"""
+    from problems import make_problem
+    p = make_problem(12, nsrc=1, seed=2)
+    o = O.Oracle(12)
+    o.set_density(p["ndens"])
+    p1, p2, p3 = 0.0319, 1.2041, 2.7519
+    avg = float(np.mean(p["ndens"], dtype=np.float64))
+    o.deterministic_clumping(p1, p2, p3, avg)
+    nd = p["ndens"].astype(np.float64)
+    want = (p1 * nd / avg * nd / avg + p2 * nd / avg + p3).astype(np.float32)
+    assert np.array_equal(o.clumping_grid, want)
+    assert o.clumping_grid.dtype == np.float32 and float(o.clumping_grid.min()) > p3
