@@ -312,6 +312,16 @@ module c2ray_b200_iface
        type(c_ptr),value :: tg
      end function c2b_set_iter_state_thermal
 
+     !> deterministic_clumping (clumping_module.F90:327-363) evaluated on the device from the resident ndens; p1..p3 =
+     !! paramsdcm(1:3) of :350, avg_dens as in :356.  A host that calls this from set_clumping instead of filling
+     !! clumping_grid itself saves the upload of the grid with every slice.
+     integer(c_int) function c2b_set_clumping_from_density(handle,p1,p2,p3,avg_dens) &
+          bind(C,name="c2b_set_clumping_from_density")
+       import
+       type(c_ptr),value :: handle
+       real(c_double),value :: p1,p2,p3,avg_dens
+     end function c2b_set_clumping_from_density
+
      !> per-source subbox counts of the last pass (with npr > 1: of every source, all-reduced), for the MPILOG
      !! diagnostics of do_source (evolve_source.F90:216-219)
      integer(c_int) function c2b_get_source_nbox(handle,nbox) bind(C,name="c2b_get_source_nbox")
