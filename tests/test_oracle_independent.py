@@ -1,0 +1,191 @@
+"""A second, independent transcription of three formulas of the reference -- written in plain Python straight from the
+Fortran text, not from oracle/c2ray_oracle.c -- compared with the C restatement on random inputs.  The reference
+cannot be run here (no Fortran compiler), so this guards the restatement against transcription slips: two independent
+readings of column_density.f90, doric.f90 and radiation_photoionrates.F90 must agree."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def _sign(a, b):
+    """Fortran sign(a,b) for integers: |a| with the sign of b, b == 0 counts as positive"""
+    return abs(a) if b >= 0 else -abs(a)
+
+
+def cinterp_py(coldensh_out, mesh, pos, srcpos, sigma, sqrt2, sqrt3):
+    """column_density.f90:29-271 (cinterp) and :276-293 (weightf); coldensh_out[k-1][j-1][i-1], positions 1-based"""
+    i, j, k = pos
+    i0, j0, k0 = srcpos
+    idel, jdel, kdel = i - i0, j - j0, k - k0                      # :78-80
+    idela, jdela, kdela = abs(idel), abs(jdel), abs(kdel)          # :81-83
+    sgni, sgnj, sgnk = _sign(1, idel), _sign(1, jdel), _sign(1, kdel)   # :86-91
+    im, jm, km = i - sgni, j - sgnj, k - sgnk                      # :92-94
+    di, dj, dk = float(idel), float(jdel), float(kdel)             # :95-97
+
+    def cd(ii, jj, kk):                                            # modulo(x-1,mesh)+1, :125-129
+        return coldensh_out[(kk - 1) % mesh[2]][(jj - 1) % mesh[1]][(ii - 1) % mesh[0]]
+
+    def weightf(c):                                                # :290
+        return 1.0 / max(0.6, c * sigma)
+
+    if kdela >= jdela and kdela >= idela:                          # :108
+        alam = (float(km - k0) + sgnk * 0.5) / dk                  # :112
+        xc = alam * di + float(i0)
+        yc = alam * dj + float(j0)
+        dx = 2.0 * abs(xc - (float(im) + 0.5 * sgni))              # :117-118
+        dy = 2.0 * abs(yc - (float(jm) + 0.5 * sgnj))
+        s1, s2, s3, s4 = (1. - dx) * (1. - dy), (1. - dy) * dx, (1. - dx) * dy, dx * dy   # :120-123
+        c1, c2, c3, c4 = cd(im, jm, km), cd(i, jm, km), cd(im, j, km), cd(i, j, km)       # :130-133
+        diag = kdela == 1 and (idela == 1 or jdela == 1)           # :152
+        both = idela == 1 and jdela == 1
+        path = math.sqrt((di * di + dj * dj) / (dk * dk) + 1.0)    # :168
+    elif jdela >= idela and jdela >= kdela:                        # :173
+        alam = (float(jm - j0) + sgnj * 0.5) / dj
+        zc = alam * dk + float(k0)
+        xc = alam * di + float(i0)
+        dz = 2.0 * abs(zc - (float(km) + 0.5 * sgnk))
+        dx = 2.0 * abs(xc - (float(im) + 0.5 * sgni))
+        s1, s2, s3, s4 = (1. - dx) * (1. - dz), (1. - dz) * dx, (1. - dx) * dz, dx * dz
+        c1, c2, c3, c4 = cd(im, jm, km), cd(i, jm, km), cd(im, jm, k), cd(i, jm, k)
+        diag = jdela == 1 and (idela == 1 or kdela == 1)
+        both = idela == 1 and kdela == 1
+        path = math.sqrt((di * di + dk * dk) / (dj * dj) + 1.0)
+    else:                                                          # :226 (idela largest)
+        alam = (float(im - i0) + sgni * 0.5) / di
+        zc = alam * dk + float(k0)
+        yc = alam * dj + float(j0)
+        dz = 2.0 * abs(zc - (float(km) + 0.5 * sgnk))
+        dy = 2.0 * abs(yc - (float(jm) + 0.5 * sgnj))
+        s1, s2, s3, s4 = (1. - dz) * (1. - dy), (1. - dz) * dy, (1. - dy) * dz, dy * dz
+        c1, c2, c3, c4 = cd(im, jm, km), cd(im, j, km), cd(im, jm, k), cd(im, j, k)
+        diag = idela == 1 and (jdela == 1 or kdela == 1)
+        both = jdela == 1 and kdela == 1
+        path = math.sqrt(1.0 + (dj * dj + dk * dk) / (di * di))
+    w1, w2, w3, w4 = s1 * weightf(c1), s2 * weightf(c2), s3 * weightf(c3), s4 * weightf(c4)
+    cdensi = (c1 * w1 + c2 * w2 + c3 * w3 + c4 * w4) / (w1 + w2 + w3 + w4)
+    if diag:
+        cdensi = (sqrt3 if both else sqrt2) * cdensi
+    return cdensi, path
+
+
+@pytest.mark.parametrize("mesh", [(16, 16, 16), (12, 17, 10)], ids=["cubic", "non_cubic"])
+def test_cinterp_second_transcription(mesh):
+    o = O.Oracle(mesh)
+    cd = o.coldensh_out
+    rng = np.random.default_rng(5)
+    cd[...] = 10.0 ** rng.uniform(15.0, 20.5, size=cd.shape)       # weightf on both sides of its 0.6 floor
+    c = O.constants()
+    n = 0
+    for _ in range(4000):
+        src = tuple(int(rng.integers(1, mesh[d] + 1)) for d in range(3))
+        # destination within the half box, possibly outside [1,mesh] (periodic wrap)
+        off = tuple(int(rng.integers(-(mesh[d] // 2), mesh[d] // 2)) for d in range(3))
+        if off == (0, 0, 0):
+            continue
+        pos = tuple(src[d] + off[d] for d in range(3))
+        v_c, p_c = o.cinterp(pos, src)
+        v_p, p_p = cinterp_py(cd, mesh, pos, src, c.sigma_HI_at_ion_freq, c.sqrt2, c.sqrt3)
+        assert p_c == pytest.approx(p_p, rel=4e-16), (pos, src)
+        assert v_c == pytest.approx(v_p, rel=1e-14), (pos, src)
+        n += 1
+    assert n > 3900
+
+
+def doric_py(dt, temp0, rhe, xfh, xfh_av, phih, clumping, c):
+    """doric.f90:33-134 for hydrogen"""
+    brech0 = clumping * c.bh00 * (temp0 / 1e4) ** c.albpow          # :74
+    sqrtt0 = math.sqrt(temp0)                                      # :76
+    acolh0 = c.colh0 * sqrtt0 * math.exp(-c.temph0 / temp0)        # :77
+    aih0 = phih + rhe * acolh0                                     # :80
+    delth = aih0 + rhe * brech0                                    # :83
+    eqxfh1 = aih0 / delth                                          # :84
+    eqxfh0 = rhe * brech0 / delth                                  # :85
+    deltht = delth * dt                                            # :88
+    ee = math.exp(-deltht)                                         # :89
+    x1 = (xfh[1] - eqxfh1) * ee + eqxfh1                           # :90
+    x0 = (xfh[0] - eqxfh0) * ee + eqxfh0                           # :91
+    if x0 < c.epsilon:                                             # :97-100
+        x0 = c.epsilon
+        x1 = 1.0 - c.epsilon
+    avg_factor = 1.0 if deltht < 1.0e-8 else (1.0 - ee) / deltht   # :104-108
+    xav1 = eqxfh1 + (xfh[1] - eqxfh1) * avg_factor                 # :112
+    xav0 = 1.0 - xav1                                              # :113
+    if xav0 < c.epsilon:                                           # :119
+        xav0 = c.epsilon
+    return (x0, x1), (xav0, xav1)
+
+
+def test_doric_second_transcription():
+    o = O.Oracle(8)
+    c = O.constants()
+    rng = np.random.default_rng(11)
+    for _ in range(2000):
+        dt = 10.0 ** rng.uniform(10.0, 15.0)
+        temp0 = 10.0 ** rng.uniform(2.0, 5.0)
+        rhe = 10.0 ** rng.uniform(-8.0, -2.0)
+        x1 = float(rng.uniform(1e-6, 1 - 1e-6))
+        phih = 0.0 if rng.uniform() < 0.2 else 10.0 ** rng.uniform(-20.0, -10.0)
+        clump = float(np.float32(rng.uniform(1.0, 30.0)))   # clumping is a default real (clumping_module.F90:17)
+        xfh = np.array([1.0 - x1, x1])
+        got, got_av = o.doric(dt, temp0, rhe, rhe, xfh, xfh.copy(), phih, clump)
+        want, want_av = doric_py(dt, temp0, rhe, xfh, xfh, phih, clump, c)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(got_av, want_av, rtol=1e-12, atol=1e-300)
+
+
+def photoion_rates_py(colum_in, colum_out, vol, nflux, thick, thin, c, numtau):
+    """radiation_photoionrates.F90:71-179 (photoion_rates), :184-208 (set_tau_table_positions), :212-228 (read_table),
+    :233-317 (photo_lookuptable) for one stellar source and the single frequency band the reference uses"""
+    def positions(tau):
+        ltau = math.log10(max(1.0e-20, tau))                                        # :197
+        odpos = min(float(numtau), max(0.0, 1.0 + (ltau - c.minlogtau) / c.dlogtau))   # :198-199
+        ipos = int(odpos)                                                           # :200
+        return ipos, odpos - float(ipos), min(numtau, ipos + 1)                     # :201-204
+
+    def read_table(table, p):                                                       # :224-226
+        ipos, res, ipos_p1 = p
+        return table[ipos] + (table[ipos_p1] - table[ipos]) * res
+
+    tau_in = colum_in * c.sigma_HI_at_ion_freq                                      # :109-111
+    tau_out = colum_out * c.sigma_HI_at_ion_freq                                    # :114-116
+    p_in, p_out = positions(tau_in), positions(tau_out)
+    photo_in = photo_out = photo_cell = 0.0
+    if nflux > 0.0:                                                                 # :126
+        phi_in = nflux * read_table(thick, p_in)                                    # :281-283
+        photo_in += phi_in
+        if abs(tau_out - tau_in) > float(np.float32(1.0e-7)):   # tau_photo_limit = 1.0e-7: a default-real literal (:245)
+            phi_out = nflux * read_table(thick, p_out)                              # :293-295
+            phi_all = phi_in - phi_out
+        else:
+            phi_all = nflux * (tau_out - tau_in) * read_table(thin, p_in)           # :301-304
+            phi_out = phi_in - phi_all
+        photo_out += phi_out
+        photo_cell += phi_all / vol                                                 # :314-315
+    return photo_cell, photo_in, photo_out
+
+
+def test_photoion_rates_second_transcription():
+    thick, thin, _ = O.rad_ini()
+    o = O.Oracle(8)
+    o.set_tables(thick, thin)
+    c = O.constants()
+    rng = np.random.default_rng(21)
+    assert c.tau_photo_limit == float(np.float32(1.0e-7))     # the literal 1.0e-7 is a default real
+    for n in range(6000):
+        colum_in = 0.0 if n % 50 == 0 else 10.0 ** rng.uniform(10.0, 23.0)
+        kind = n % 3
+        if kind == 0:      # optically thick cell
+            colum_out = colum_in + 10.0 ** rng.uniform(12.0, 22.0)
+        elif kind == 1:    # optically thin cell (below tau_photo_limit)
+            colum_out = colum_in + 10.0 ** rng.uniform(5.0, 10.0)
+        else:              # around the switch
+            colum_out = colum_in + 10.0 ** rng.uniform(10.0, 11.5)
+        vol = 10.0 ** rng.uniform(60.0, 75.0)
+        nflux = 0.0 if n % 97 == 0 else 10.0 ** rng.uniform(-3.0, 9.0)
+        got = o.photoion_rates(colum_in, colum_out, vol, nflux)
+        want = photoion_rates_py(colum_in, colum_out, vol, nflux, thick, thin, c, len(thick) - 1)
+        for g, w in zip(got, want):
+            assert g == pytest.approx(w, rel=1e-13, abs=0.0), (n, colum_in, colum_out)
