@@ -189,3 +189,104 @@ def test_photoion_rates_second_transcription():
         want = photoion_rates_py(colum_in, colum_out, vol, nflux, thick, thin, c, len(thick) - 1)
         for g, w in zip(got, want):
             assert g == pytest.approx(w, rel=1e-13, abs=0.0), (n, colum_in, colum_out)
+
+
+def do_source_py(p, ns, thick, thin, c):
+    """do_source (evolve_source.F90:58-221), serial branch with evolve2D (:227-267), and evolve0D
+    (evolve_point.F90:83-299) for the isothermal path with a homogeneous LLS column (type_of_LLS 1) or none;
+    periodic boundaries.  Returns (coldensh_out, phih_grid, nbox, photon_loss_src, number of evolve0D updates)."""
+    mesh = p["mesh"]
+    ndens, xh_av = p["ndens"], p["xh"]
+    dr, vol = p["dr"], p["vol"]
+    src = [int(v) for v in p["srcpos"][ns - 1]]
+    nflux = float(p["normflux"][ns - 1])
+    subboxsize, max_subbox = 5, 1000                                  # c2ray_parameters.f90:54,61
+    max_coldensh = float(np.float32(2e19))                            # evolve_point.F90:95 (a default-real literal)
+    coldensh_out = np.zeros((mesh[2], mesh[1], mesh[0]))              # evolve_source.F90:90
+    phih = np.zeros_like(coldensh_out)
+    lastpos_r = [src[d] + min(max_subbox, mesh[d] // 2 - 1 + mesh[d] % 2) for d in range(3)]   # :100
+    lastpos_l = [src[d] - min(max_subbox, mesh[d] // 2) for d in range(3)]                       # :101
+    state = {"loss": 0.0, "updates": 0}
+
+    def evolve0d(rtpos, last_l, last_r):
+        pos = [(rtpos[d] - 1) % mesh[d] for d in range(3)]            # 0-based modulo(rtpos-1,mesh), evolve_point.F90:122-124
+        idx = (pos[2], pos[1], pos[0])
+        if coldensh_out[idx] != 0.0:                                  # :128
+            return
+        state["updates"] += 1
+        h_av1 = max(float(xh_av[idx]), c.epsilon)                     # :137
+        h_av0 = max(1.0 - h_av1, c.epsilon)                           # :140
+        ndens_p = float(ndens[idx])                                   # :146
+        stop = False
+        if rtpos == src:                                              # :151-160
+            coldensh_in = 0.0
+            path = 0.5 * dr[0]
+            vol_ph = dr[0] * dr[1] * dr[2]
+        else:
+            coldensh_in, path = cinterp_py(coldensh_out, mesh, tuple(rtpos), tuple(src), c.sigma_HI_at_ion_freq,
+                                           c.sqrt2, c.sqrt3)          # :165
+            path = path * dr[0]                                       # :167
+            xs = dr[0] * float(rtpos[0] - src[0])                     # :170-172
+            ys = dr[1] * float(rtpos[1] - src[1])
+            zs = dr[2] * float(rtpos[2] - src[2])
+            dist2 = xs * xs + ys * ys + zs * zs                       # :173
+            vol_ph = 4.0 * c.pi * dist2 * path                        # :177
+            if p["use_LLS"]:                                          # :186-197, type_of_LLS == 1
+                coldensh_in = coldensh_in + p["coldensh_LLS"] * path / dr[0]
+        if coldensh_in > max_coldensh:                                # :201
+            stop = True
+        coldensh_out[idx] = coldensh_in + h_av0 * ndens_p * path      # :247-248 with coldens, doric.f90:153
+        photo_out = 0.0
+        if not stop:                                                  # :254-262
+            cell, _, photo_out = photoion_rates_py(coldensh_in, coldensh_out[idx], vol_ph, nflux, thick, thin, c,
+                                                   len(thick) - 1)
+            phih[idx] += cell / (h_av0 * ndens_p)                     # :262, :283-284
+        if any(rtpos[d] == last_l[d] for d in range(3)) or any(rtpos[d] == last_r[d] for d in range(3)):   # :290-291
+            state["loss"] += photo_out * vol / vol_ph                 # :292-293
+
+    nbox = 0
+    total_source_flux = nflux * p["S_star"]                           # evolve_source.F90:119
+    photon_loss_src = total_source_flux                               # :121
+    last_r, last_l = list(src), list(src)                             # :122-123
+    while photon_loss_src > c.loss_fraction * total_source_flux and last_r[2] < lastpos_r[2] and \
+            last_l[2] > lastpos_l[2]:                                 # :128-131
+        nbox += 1
+        state["loss"] = 0.0
+        last_r = [min(src[d] + subboxsize * nbox, lastpos_r[d]) for d in range(3)]   # :135
+        last_l = [max(src[d] - subboxsize * nbox, lastpos_l[d]) for d in range(3)]   # :136
+        ks = list(range(src[2], last_r[2] + 1)) + list(range(src[2] - 1, last_l[2] - 1, -1))   # :190-199
+        for k in ks:
+            js = list(range(src[1], last_r[1] + 1)) + list(range(src[1] - 1, last_l[1] - 1, -1))   # evolve2D, :241-263
+            for j in js:
+                for i in list(range(src[0], last_r[0] + 1)) + list(range(src[0] - 1, last_l[0] - 1, -1)):
+                    evolve0d([i, j, k], last_l, last_r)
+        photon_loss_src = state["loss"]                               # :206
+    return coldensh_out, phih, nbox, photon_loss_src, state["updates"]
+
+
+@pytest.mark.parametrize("case", [dict(N=14, seed=3, state="random", use_LLS=True),
+                                  dict(N=13, seed=4, state="random", use_LLS=False),
+                                  dict(N=(12, 15, 10), seed=6, state="ionized", use_LLS=True)],
+                         ids=["even_lls", "odd", "non_cubic_ionized"])
+def test_do_source_second_transcription(case):
+    """a whole single-source trace: the serial sweep, the growing subbox with its loss cut-off, the periodic half box
+    (incl. the extra layer on the negative side of an even mesh), evolve0D with cinterp and the rate look-up"""
+    from problems import make_problem, setup_oracle
+    p = make_problem(case["N"], nsrc=3, seed=case["seed"], state=case["state"], use_LLS=case["use_LLS"], flux=3e7)
+    if case["state"] == "random":
+        p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    thick, thin, _ = O.rad_ini()
+    c = O.constants()
+    o = setup_oracle(p)
+    o.xh_av[...] = p["xh"]
+    for ns in (1, 2, 3):
+        o.set_rates_to_zero()
+        o.coldensh_out[...] = 0.0
+        r = o.do_source(ns)
+        cd, ph, nbox, loss, upd = do_source_py(p, ns, thick, thin, c)
+        assert (r.nbox, r.updates) == (nbox, upd)
+        assert np.array_equal(o.coldensh_out != 0, cd != 0)
+        np.testing.assert_allclose(o.coldensh_out, cd, rtol=1e-13, atol=0)
+        assert np.array_equal(o.phih != 0, ph != 0)
+        np.testing.assert_allclose(o.phih, ph, rtol=1e-10, atol=0)   # Gamma_in - Gamma_out cancels at small dtau
+        assert r.photon_loss_src == pytest.approx(loss, rel=1e-10)
