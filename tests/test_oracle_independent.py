@@ -290,3 +290,60 @@ def test_do_source_second_transcription(case):
         assert np.array_equal(o.phih != 0, ph != 0)
         np.testing.assert_allclose(o.phih, ph, rtol=1e-10, atol=0)   # Gamma_in - Gamma_out cancels at small dtau
         assert r.photon_loss_src == pytest.approx(loss, rel=1e-10)
+
+
+def global_pass_py(p, xh, xh_av, xh_intermed, phih, dt, c, temper):
+    """global_pass's loop (evolve.F90:548-555) over evolve0D_global (evolve_point.F90:305-406) and do_chemistry
+    (:410-555), isothermal; electrondens is tped.f90:75-83.  Returns (conv_flag, new xh_intermed, new xh_av)."""
+    new_int, new_av = xh_intermed.copy(), xh_av.copy()
+    conv_flag = 0
+    eps, mfc, mfa = c.epsilon, c.minimum_fractional_change, c.minimum_fraction_of_atoms
+    for idx in np.ndindex(xh.shape):
+        h_old1 = max(eps, float(xh[idx]))                          # evolve_point.F90:349
+        h_av1 = max(eps, float(xh_av[idx]))                        # :350
+        h_old0 = 1.0 - h_old1                                      # :352
+        h_av0 = 1.0 - h_av1                                        # :353
+        ndens_p = float(p["ndens"][idx])                           # :357
+        ph = float(phih[idx])                                      # :363
+        clump = float(p["clumping_grid"][idx]) if p["clumping_grid"] is not None else float(np.float32(p["clumping"]))   # :441-443
+        nit = 0
+        while True:                                                # :448
+            nit += 1
+            yh0_av_old = h_av0                                     # :453
+            de = ndens_p * (h_av1 + c.abu_c)                       # :461, tped.f90:81
+            (h0, h1), (h_av0, h_av1) = doric_py(dt, temper, de, (h_old0, h_old1), None, ph, clump, c)   # :457, :513
+            if abs((h_av0 - yh0_av_old) / h_av0) < mfc or h_av0 < mfa:   # :530-535 (the temperature term is 0 < mfc)
+                break
+            if nit > 400:                                          # :540
+                break
+        yh1_prev = max(eps, float(xh_av[idx]))                     # :376
+        yh0_prev = 1.0 - yh1_prev                                  # :377
+        if abs(h_av0 - yh0_prev) > mfc and abs((h_av0 - yh0_prev) / h_av0) > mfc and h_av0 > mfa:   # :382-384
+            conv_flag += 1                                         # :389
+        new_int[idx] = h1                                          # :400
+        new_av[idx] = h_av1                                        # :401
+    return conv_flag, new_int, new_av
+
+
+@pytest.mark.parametrize("clumping", ["scalar", "scalar2", "grid"])
+def test_global_pass_second_transcription(clumping):
+    from problems import make_problem, setup_oracle
+    p = make_problem(10, nsrc=3, seed=8, state="random", use_LLS=True, clumping=clumping, flux=3e7)
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    c = O.constants()
+    o = setup_oracle(p)
+    o.xh_av[...] = p["xh"]
+    o.xh_intermed[...] = p["xh"]
+    o.state_before()
+    o.set_rates_to_zero()
+    r = o.pass_all_sources()
+    phih = o.phih.copy()
+    dt = 1e6 * c.YEAR
+    for it in range(2):    # two per-cell passes with the same rates: the second starts from the first one's xh_av
+        xh_av_in, xh_int_in = o.xh_av.copy(), o.xh_intermed.copy()
+        conv, want_int, want_av = global_pass_py(p, o.xh.copy(), xh_av_in, xh_int_in, phih, dt, c, p["temper"])
+        g = o.global_pass(dt, r.photon_loss_all)
+        assert g.conv_flag == conv
+        np.testing.assert_allclose(o.xh_intermed, want_int, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(o.xh_av, want_av, rtol=0, atol=1e-14)
+    assert conv < 1000
