@@ -347,3 +347,57 @@ def test_global_pass_second_transcription(clumping):
         np.testing.assert_allclose(o.xh_intermed, want_int, rtol=0, atol=1e-14)
         np.testing.assert_allclose(o.xh_av, want_av, rtol=0, atol=1e-14)
     assert conv < 1000
+
+
+def evolve3d_py(p, dt, thick, thin, c):
+    """evolve3D (evolve.F90:83-281), restart == 0, one rank: the outer iteration over pass_all_sources (:444-495, sources
+    in file order) and global_pass (:499-573) with its two ways of ending.  Returns (niter, conv_flag per iteration,
+    xh, xh_av)."""
+    mesh = p["mesh"]
+    ncell = mesh[0] * mesh[1] * mesh[2]
+    xh = p["xh"].copy()
+    xh_av, xh_intermed = xh.copy(), xh.copy()                       # :140-147
+    niter = 0                                                       # :148
+    conv_flag = ncell                                               # :149
+    prev1 = prev0 = float(np.float32(2.0) * np.float32(mesh[0]) * np.float32(mesh[1]) * np.float32(mesh[2]))   # :150-151
+    nsrc = len(p["normflux"])
+    conv_criterion = min(int(c.convergence_fraction * mesh[0] * mesh[1] * mesh[2]), (nsrc - 1) // 3)   # :162
+    flags = []
+    q = dict(p)
+    while True:
+        s1 = float(np.sum(xh_intermed))                             # :183
+        s0 = float(np.float32(ncell)) - s1                          # :184
+        rel1 = abs(s1 - prev1) / s1 if s1 > 0.0 else 1.0            # :187-191
+        rel0 = abs(s0 - prev0) / s0 if s0 > 0.0 else 1.0            # :192-196
+        if conv_flag < conv_criterion or (rel1 < c.convergence_fraction and rel0 < c.convergence_fraction):   # :212-214
+            xh = xh_intermed.copy()                                 # :215-217
+            break
+        if niter > 100:                                             # :228
+            break
+        prev1, prev0 = s1, s0                                       # :236-237
+        niter += 1                                                  # :240
+        phih = np.zeros_like(xh)                                    # set_rates_to_zero, :430-440
+        q["xh"] = xh_av                                             # evolve0D reads xh_av (evolve_point.F90:137)
+        for ns in range(1, nsrc + 1):                               # pass_all_sources / do_grid, one rank
+            phih += do_source_py(q, ns, thick, thin, c)[1]
+        conv_flag, xh_intermed, xh_av = global_pass_py(p, xh, xh_av, xh_intermed, phih, dt, c, p["temper"])   # :269
+        flags.append(conv_flag)
+    return niter, flags, xh, xh_av
+
+
+def test_evolve3d_second_transcription():
+    """a whole evolve3D step in plain Python against the C restatement: number of outer iterations, the convergence
+    counter of every iteration, final fractions"""
+    from problems import make_problem, setup_oracle
+    p = make_problem(9, nsrc=4, seed=12, state="random", use_LLS=True, flux=3e7)
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    thick, thin, _ = O.rad_ini()
+    c = O.constants()
+    dt = 1e6 * c.YEAR
+    o = setup_oracle(p)
+    ro = o.evolve3D(dt)
+    niter, flags, xh, xh_av = evolve3d_py(p, dt, thick, thin, c)
+    assert niter == ro.niter and niter >= 2
+    assert flags == list(ro.conv_flag[1:ro.niter + 1])
+    np.testing.assert_allclose(o.xh, xh, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o.xh_av, xh_av, rtol=0, atol=1e-12)
