@@ -401,3 +401,24 @@ def test_evolve3d_second_transcription():
     assert flags == list(ro.conv_flag[1:ro.niter + 1])
     np.testing.assert_allclose(o.xh, xh, rtol=0, atol=1e-12)
     np.testing.assert_allclose(o.xh_av, xh_av, rtol=0, atol=1e-12)
+
+
+def test_photo_tables_against_independent_quadrature():
+    """stellar_photo_thick_table(tau) = S_star * int SED exp(-tau*s) dnu / int SED dnu and the thin table with one more
+    factor s = (nu/nu_HI)^-2.8 (radiation_tables.F90:361-430, 524-543) for the 5e4 K black body.  The reference
+    integrates 128 Romberg intervals over [nu_HI, 40 nu_HI]; against a fine trapezoid rule that coarse grid is good to
+    0.5 % where the integrand peaks at the edge (small and moderate tau) and to 2e-5 at the largest tau -- the tolerance here is the
+    reference's own quadrature error, which the restatement reproduces bit for bit (test_oracle.py, Appendix D)."""
+    from c2ray3dm_b200 import constants as K
+    thick, thin, d = O.rad_ini()
+    assert d.freq_min == K.bb_MinFreq and d.freq_max == K.bb_MaxFreq
+    nu = np.linspace(d.freq_min, d.freq_max, 400001)
+    x = nu * K.hplanck / (K.k_B * K.bb_Teff)
+    sed = nu * nu / np.expm1(x)
+    cs = (nu / d.freq_min) ** (-K.pl_index_cross_section_HI)
+    norm = np.trapezoid(sed, nu)
+    for it, tol in ((0, 6e-3), (1, 6e-3), (1000, 6e-3), (1500, 6e-3), (1668, 6e-3), (1700, 6e-3), (1800, 3e-3), (1900, 1e-3),
+                    (2000, 1e-4)):
+        tau = 0.0 if it == 0 else 10.0 ** (-20.0 + 0.012 * (it - 1))
+        assert thick[it] / thick[0] == pytest.approx(np.trapezoid(sed * np.exp(-tau * cs), nu) / norm, rel=tol)
+        assert thin[it] / thick[0] == pytest.approx(np.trapezoid(sed * cs * np.exp(-tau * cs), nu) / norm, rel=tol)
