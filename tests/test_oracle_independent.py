@@ -349,12 +349,40 @@ def test_global_pass_second_transcription(clumping):
     assert conv < 1000
 
 
+def photon_statistics_py(p, xh_before, xh, xh_av, photon_loss_all, dt, c):
+    """state_before / state_after / total_rates / total_ionizations / report_photonstatistics
+    (photonstatistics.F90:104-281) for the isothermal case; LLS_loss stays 0 in the reference (evolve0D passes the
+    never-assigned phi%photo_in_HI to total_LLS_loss, evolve_point.F90:273-274)"""
+    nd = p["ndens"].astype(np.float64)
+    mesh = p["mesh"]
+    vol = p["vol"]
+    clump = p["clumping_grid"].astype(np.float64) if p["clumping_grid"] is not None else float(np.float32(p["clumping"]))
+    T = p["temper"]
+    st = {}
+    st["h0_before"] = float(np.sum(nd * (1.0 - xh_before))) * vol            # :118-131
+    st["h0_after"] = float(np.sum(nd * (1.0 - xh))) * vol                    # :204-216
+    st["h1_after"] = float(np.sum(nd * xh)) * vol
+    yh1, yh0 = xh_av, 1.0 - xh_av                                            # total_rates(dt,xh_av), :155-163
+    ne = nd * (yh1 + c.abu_c)                                                # tped.f90:81
+    st["totrec"] = float(np.sum(nd * yh1 * ne * clump * c.bh00 * (T / 1e4) ** c.albpow)) * vol * dt      # :170-172,:183
+    st["totcollisions"] = float(np.sum(nd * yh0 * ne * c.colh0 * math.sqrt(T) * math.exp(-c.temph0 / T))) * vol * dt
+    st["dh0"] = st["h0_before"] - st["h0_after"]                             # :224
+    st["total_ion"] = st["totrec"] + st["dh0"]                               # :225
+    m3 = float(np.float32(mesh[0]) * np.float32(mesh[1]) * np.float32(mesh[2]))
+    photon_loss = photon_loss_all / m3                                       # evolve.F90:525
+    st["total_photon_loss"] = photon_loss * dt * m3                          # :262-263
+    st["totalsrc"] = float(np.sum(p["normflux"])) * p["S_star"] * dt         # :265
+    st["photcons"] = (st["total_ion"] + 0.0 - st["totcollisions"]) / st["totalsrc"]   # :266
+    return st
+
+
 def evolve3d_py(p, dt, thick, thin, c):
     """evolve3D (evolve.F90:83-281), restart == 0, one rank: the outer iteration over pass_all_sources (:444-495, sources
-    in file order) and global_pass (:499-573) with its two ways of ending.  Returns (niter, conv_flag per iteration,
-    xh, xh_av)."""
+    in file order) and global_pass (:499-573) with its two ways of ending, then the photon statistics of the step.
+    Returns (niter, conv_flag per iteration, xh, xh_av, statistics)."""
     mesh = p["mesh"]
     ncell = mesh[0] * mesh[1] * mesh[2]
+    xh_before = p["xh"].copy()
     xh = p["xh"].copy()
     xh_av, xh_intermed = xh.copy(), xh.copy()                       # :140-147
     niter = 0                                                       # :148
@@ -364,6 +392,7 @@ def evolve3d_py(p, dt, thick, thin, c):
     conv_criterion = min(int(c.convergence_fraction * mesh[0] * mesh[1] * mesh[2]), (nsrc - 1) // 3)   # :162
     flags = []
     q = dict(p)
+    photon_loss_all = 0.0
     while True:
         s1 = float(np.sum(xh_intermed))                             # :183
         s0 = float(np.float32(ncell)) - s1                          # :184
@@ -377,30 +406,39 @@ def evolve3d_py(p, dt, thick, thin, c):
         prev1, prev0 = s1, s0                                       # :236-237
         niter += 1                                                  # :240
         phih = np.zeros_like(xh)                                    # set_rates_to_zero, :430-440
+        photon_loss_all = 0.0
         q["xh"] = xh_av                                             # evolve0D reads xh_av (evolve_point.F90:137)
         for ns in range(1, nsrc + 1):                               # pass_all_sources / do_grid, one rank
-            phih += do_source_py(q, ns, thick, thin, c)[1]
+            r = do_source_py(q, ns, thick, thin, c)
+            phih += r[1]
+            photon_loss_all = photon_loss_all + r[3]                # photon_loss(1)=photon_loss(1)+photon_loss_src
         conv_flag, xh_intermed, xh_av = global_pass_py(p, xh, xh_av, xh_intermed, phih, dt, c, p["temper"])   # :269
         flags.append(conv_flag)
-    return niter, flags, xh, xh_av
+    stats = photon_statistics_py(p, xh_before, xh, xh_av, photon_loss_all, dt, c)   # :277-279
+    return niter, flags, xh, xh_av, stats
 
 
-def test_evolve3d_second_transcription():
+@pytest.mark.parametrize("clumping", ["scalar", "grid"])
+def test_evolve3d_second_transcription(clumping):
     """a whole evolve3D step in plain Python against the C restatement: number of outer iterations, the convergence
-    counter of every iteration, final fractions"""
+    counter of every iteration, final fractions, the photon-conservation statistics"""
     from problems import make_problem, setup_oracle
-    p = make_problem(9, nsrc=4, seed=12, state="random", use_LLS=True, flux=3e7)
+    p = make_problem(9, nsrc=4, seed=12, state="random", use_LLS=True, flux=3e7, clumping=clumping)
     p["xh"] = 1 - (1 - p["xh"]) * 1e-2
     thick, thin, _ = O.rad_ini()
     c = O.constants()
     dt = 1e6 * c.YEAR
     o = setup_oracle(p)
     ro = o.evolve3D(dt)
-    niter, flags, xh, xh_av = evolve3d_py(p, dt, thick, thin, c)
+    niter, flags, xh, xh_av, stats = evolve3d_py(p, dt, thick, thin, c)
     assert niter == ro.niter and niter >= 2
     assert flags == list(ro.conv_flag[1:ro.niter + 1])
     np.testing.assert_allclose(o.xh, xh, rtol=0, atol=1e-12)
     np.testing.assert_allclose(o.xh_av, xh_av, rtol=0, atol=1e-12)
+    for name, want in stats.items():
+        tol = 1e-9 if name in ("dh0", "total_ion", "photcons") else 1e-11   # differences of nearly equal sums
+        assert getattr(ro.final_stats, name) == pytest.approx(want, rel=tol), name
+    assert ro.final_stats.LLS_loss == 0.0
 
 
 def test_photo_tables_against_independent_quadrature():
