@@ -118,7 +118,7 @@ class Evolve:
         return a, b
 
     def set_cooling_table(self, log10_temp, log10_cool):
-        """the 61 rows of tables/corocool.tab (cooling.f90:62-90)"""
+        """the 61 rows of tables/corocool.tab (cooling.f90:64-87)"""
         a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (log10_temp, log10_cool))
         self._ck(self.L.c2b_set_cooling_table(self.h, _dp(a), _dp(b), a.size), "c2b_set_cooling_table")
 

@@ -147,7 +147,7 @@ contains
 
   end subroutine b200_init
 
-  !> the 61 rows of tables/corocool.tab, read as setup_cool does (cooling.f90:62-90): the module
+  !> the 61 rows of tables/corocool.tab, read as setup_cool does (cooling.f90:64-87): the module
   !! radiative_cooling keeps its table private, so the shim reads the file itself
   subroutine b200_upload_cooling_table ()
     real(kind=dp) :: temp(61), cool(61)

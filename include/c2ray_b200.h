@@ -167,7 +167,7 @@ int c2b_set_xh(c2b_handle *h, const double *xh);                        /* ionfr
  * itself when the handle is not isothermal, c2b_get_heat_tables reads them back */
 int c2b_set_heat_tables(c2b_handle *h, const double *heat_thick, const double *heat_thin, int32_t n);
 int c2b_get_heat_tables(c2b_handle *h, double *heat_thick, double *heat_thin);
-/* the 61 rows (log10 T, log10 Lambda) of tables/corocool.tab as setup_cool reads them (cooling.f90:62-90) */
+/* the 61 rows (log10 T, log10 Lambda) of tables/corocool.tab as setup_cool reads them (cooling.f90:64-87) */
 int c2b_set_cooling_table(c2b_handle *h, const double *log10_temp, const double *log10_cool, int32_t n /* 61 */);
 int c2b_set_redshift(c2b_handle *h, double zred);                       /* cosmology.F90:42 (cosmo_cool) */
 /* temperature_grid(mesh)%(current,average,intermed), default real (temperature_module.F90:21-35): 3 floats per

@@ -447,7 +447,7 @@ void orc_set_heat_tables(orc_state *s, const double *heat_thick, const double *h
   memcpy(s->heat_thick, heat_thick, sizeof(s->heat_thick));
   memcpy(s->heat_thin, heat_thin, sizeof(s->heat_thin));
 }
-/* setup_cool cooling.f90:62-90: 61 rows (log10 T, log10 Lambda) of tables/corocool.tab */
+/* setup_cool cooling.f90:64-87: 61 rows (log10 T, log10 Lambda) of tables/corocool.tab */
 void orc_set_cooling_table(orc_state *s, const double *log10_temp, const double *log10_cool) {
   s->cool_mintemp = log10_temp[0];
   s->cool_dtemp = log10_temp[1] - log10_temp[0];

@@ -353,7 +353,7 @@ class Oracle:
         self.L.orc_set_heat_tables(self.h, _dp(a), _dp(b))
 
     def set_cooling_table(self, log10_temp, log10_cool):
-        """the 61 rows of tables/corocool.tab (cooling.f90:62-90)"""
+        """the 61 rows of tables/corocool.tab (cooling.f90:64-87)"""
         a, b = (np.ascontiguousarray(x, dtype=np.float64) for x in (log10_temp, log10_cool))
         assert a.size == 61 and b.size == 61
         self.L.orc_set_cooling_table(self.h, _dp(a), _dp(b))
