@@ -156,7 +156,7 @@ def photoion_rates_py(colum_in, colum_out, vol, nflux, thick, thin, c, numtau):
     if nflux > 0.0:                                                                 # :126
         phi_in = nflux * read_table(thick, p_in)                                    # :281-283
         photo_in += phi_in
-        if abs(tau_out - tau_in) > float(np.float32(1.0e-7)):   # tau_photo_limit = 1.0e-7: a default-real literal (:245)
+        if abs(tau_out - tau_in) > float(np.float32(1.0e-7)):   # tau_photo_limit = 1.0e-7: a default-real literal (:244)
             phi_out = nflux * read_table(thick, p_out)                              # :293-295
             phi_all = phi_in - phi_out
         else:
