@@ -191,7 +191,28 @@ def test_photoion_rates_second_transcription():
             assert g == pytest.approx(w, rel=1e-13, abs=0.0), (n, colum_in, colum_out)
 
 
-def do_source_py(p, ns, thick, thin, c):
+def heat_lookup_py(colum_in, colum_out, vol, nflux, hthick, hthin, c, numtau):
+    """heat_lookuptable (radiation_photoionrates.F90:323-417) as photoion_rates calls it for isothermal=.false. (:136-147)"""
+    def positions(tau):                                                             # set_tau_table_positions, :184-208
+        odpos = min(float(numtau), max(0.0, 1.0 + (math.log10(max(1.0e-20, tau)) - c.minlogtau) / c.dlogtau))
+        ipos = int(odpos)
+        return ipos, odpos - float(ipos), min(numtau, ipos + 1)
+
+    def read_table(table, q):
+        return table[q[0]] + (table[q[2]] - table[q[0]]) * q[1]
+
+    tau_in, tau_out = colum_in * c.sigma_HI_at_ion_freq, colum_out * c.sigma_HI_at_ion_freq
+    tau_cell = (colum_out - colum_in) * c.sigma_HI_at_ion_freq                      # :138-140 (colum_cell_HI, :106)
+    if not nflux > 0.0:                                                             # :143
+        return 0.0
+    heat_in = nflux * read_table(hthick, positions(tau_in))                         # :377-378
+    if abs(tau_out - tau_in) > float(np.float32(1.0e-4)):                           # tau_heat_limit, :333 (default real)
+        heat_out = nflux * read_table(hthick, positions(tau_out))                   # :383-384
+        return (heat_in - heat_out) / vol                                           # :385
+    return nflux * tau_cell * read_table(hthin, positions(tau_in)) / vol            # :390-393
+
+
+def do_source_py(p, ns, thick, thin, c, heat=None):
     """do_source (evolve_source.F90:58-221), serial branch with evolve2D (:227-267), and evolve0D
     (evolve_point.F90:83-299) for the isothermal path with a homogeneous LLS column (type_of_LLS 1) or none;
     periodic boundaries.  Returns (coldensh_out, phih_grid, nbox, photon_loss_src, number of evolve0D updates)."""
@@ -204,6 +225,7 @@ def do_source_py(p, ns, thick, thin, c):
     max_coldensh = float(np.float32(2e19))                            # evolve_point.F90:95 (a default-real literal)
     coldensh_out = np.zeros((mesh[2], mesh[1], mesh[0]))              # evolve_source.F90:90
     phih = np.zeros_like(coldensh_out)
+    phiheat = np.zeros_like(coldensh_out)
     lastpos_r = [src[d] + min(max_subbox, mesh[d] // 2 - 1 + mesh[d] % 2) for d in range(3)]   # :100
     lastpos_l = [src[d] - min(max_subbox, mesh[d] // 2) for d in range(3)]                       # :101
     state = {"loss": 0.0, "updates": 0}
@@ -241,6 +263,9 @@ def do_source_py(p, ns, thick, thin, c):
             cell, _, photo_out = photoion_rates_py(coldensh_in, coldensh_out[idx], vol_ph, nflux, thick, thin, c,
                                                    len(thick) - 1)
             phih[idx] += cell / (h_av0 * ndens_p)                     # :262, :283-284
+            if heat is not None:                                      # :285-286: not divided by the neutral density
+                phiheat[idx] += heat_lookup_py(coldensh_in, coldensh_out[idx], vol_ph, nflux, heat[0], heat[1], c,
+                                               len(thick) - 1)
         if any(rtpos[d] == last_l[d] for d in range(3)) or any(rtpos[d] == last_r[d] for d in range(3)):   # :290-291
             state["loss"] += photo_out * vol / vol_ph                 # :292-293
 
@@ -261,6 +286,8 @@ def do_source_py(p, ns, thick, thin, c):
                 for i in list(range(src[0], last_r[0] + 1)) + list(range(src[0] - 1, last_l[0] - 1, -1)):
                     evolve0d([i, j, k], last_l, last_r)
         photon_loss_src = state["loss"]                               # :206
+    if heat is not None:
+        return coldensh_out, phih, nbox, photon_loss_src, state["updates"], phiheat
     return coldensh_out, phih, nbox, photon_loss_src, state["updates"]
 
 
@@ -460,3 +487,136 @@ def test_photo_tables_against_independent_quadrature():
         tau = 0.0 if it == 0 else 10.0 ** (-20.0 + 0.012 * (it - 1))
         assert thick[it] / thick[0] == pytest.approx(np.trapezoid(sed * np.exp(-tau * cs), nu) / norm, rel=tol)
         assert thin[it] / thick[0] == pytest.approx(np.trapezoid(sed * cs * np.exp(-tau * cs), nu) / norm, rel=tol)
+
+
+
+def thermal_py(dt, T_initial, T_final, T_average, ndens_electron, ndens_atom, h_old1, h_av1, h1, heating, cool, c, zred,
+               cosmological):
+    """thermal (thermal.f90:22-176) with temper2pressr / pressr2temper (tped.f90:41-70), coolin (cooling.f90:38-59)
+    and cosmo_cool (cosmology.F90:198-225).  Returns (final, average); both unchanged when T_initial <= minitemp."""
+    mintemp, dtemp, cie = cool
+    gamma1 = 5.0 / 3.0 - 1.0                                              # atomic.f90:23-25
+    minitemp, relative_denergy = 1.0, float(np.float32(0.1))             # c2ray_parameters.f90:108,110
+    el = lambda x1: ndens_atom * (x1 + c.abu_c)                           # electrondens, tped.f90:81
+    internal_energy = (ndens_atom + el(h_old1)) * c.k_B * T_initial / gamma1      # thermal.f90:75-76
+    if cosmological:                                                      # :81-85
+        dzdt = c.H0 * (1. + zred) * math.sqrt(c.Omega0 * (1. + zred) ** 3 + 1. - c.Omega0)   # cosmology.F90:217
+        cosmo_cool_rate = internal_energy * 2.0 / (1.0 + zred) * dzdt     # :220
+    else:
+        cosmo_cool_rate = 0.0
+    if not T_initial > minitemp:                                          # :88
+        return T_final, T_average
+    cumulative_time = 0.0
+    i_heating = 0
+    T_average = 0.0
+    T_mid = T_initial
+    while True:
+        i_heating += 1
+        tpos = (math.log10(T_mid) - mintemp) / dtemp + 1.0                # coolin, cooling.f90:49-52
+        itpos = min(61 - 1, max(1, int(tpos)))
+        dtpos = tpos - float(itpos)
+        itpos1 = min(61, itpos + 1)
+        cooling = ndens_atom * ndens_electron * (cie[itpos - 1] + (cie[itpos1 - 1] - cie[itpos - 1]) * dtpos) \
+            + cosmo_cool_rate                                             # thermal.f90:104-105
+        thermal_rate = max(1e-50, abs(cooling - heating))                 # :108
+        thermal_timescale = internal_energy / abs(thermal_rate)           # :109
+        dt_thermal = relative_denergy * thermal_timescale                 # :112
+        dt_ode = min(dt_thermal, dt - cumulative_time)                    # :113
+        internal_energy = internal_energy + dt_ode * (heating - cooling)  # :116
+        T_average = T_average + 0.5 * T_mid * dt_ode                      # :119-120
+        T_mid = internal_energy * gamma1 / (c.k_B * (ndens_atom + el(h_av1)))     # :123-124
+        T_average = T_average + 0.5 * T_mid * dt_ode                      # :125-126
+        if T_mid < minitemp:                                              # :129-133 (no division by gamma1 there)
+            internal_energy = (ndens_atom + el(h_av1)) * c.k_B * minitemp
+            T_mid = minitemp
+        cumulative_time = cumulative_time + dt_ode                        # :136
+        if cumulative_time >= dt or abs(cumulative_time - dt) < float(np.float32(1e-6)) * dt:   # :141
+            break
+        if i_heating > 10000:                                             # :144
+            break
+    T_average = T_average / dt if dt > 0.0 else T_initial                 # :148-152
+    T_final = internal_energy * gamma1 / (c.k_B * (ndens_atom + el(h1)))  # :155-156
+    return T_final, T_average
+
+
+def global_pass_thermal_py(p, xh, xh_av, xh_intermed, phih, phiheat, Tgrid, dt, c, cool, zred, cosmological):
+    """evolve0D_global + do_chemistry (evolve_point.F90:305-555) with isothermal=.false.; Tgrid[...,0:3] = current,
+    average, intermed as default reals (temperature_module.F90:21-31,134-169).  Updates Tgrid in place."""
+    new_int, new_av = xh_intermed.copy(), xh_av.copy()
+    conv_flag = 0
+    eps, mfc, mfa = c.epsilon, c.minimum_fractional_change, c.minimum_fraction_of_atoms
+    for idx in np.ndindex(xh.shape):
+        h_old1 = max(eps, float(xh[idx]))
+        h_av1 = max(eps, float(xh_av[idx]))
+        h_old0, h_av0 = 1.0 - h_old1, 1.0 - h_av1
+        ndens_p = float(p["ndens"][idx])
+        T_start = [float(Tgrid[idx + (k,)]) for k in range(3)]            # get_temperature_point, :358 (current, average, intermed)
+        ph, heat = float(phih[idx]), float(phiheat[idx])                  # :363-364
+        clump = float(p["clumping_grid"][idx]) if p["clumping_grid"] is not None else float(np.float32(p["clumping"]))
+        T_end_cur, T_end_avg, T_end_int = T_start                         # temperature_end=temperature_start, :437-438
+        nit = 0
+        while True:
+            nit += 1
+            yh0_av_old = h_av0
+            de = ndens_p * (h_av1 + c.abu_c)
+            (h0, h1), (h_av0, h_av1) = doric_py(dt, T_end_avg, de, (h_old0, h_old1), None, ph, clump, c)   # :513-514
+            de = ndens_p * (h_av1 + c.abu_c)                              # :516
+            T_end_int, T_end_avg = thermal_py(dt, T_start[0], T_end_int, T_end_avg, de, ndens_p, h_old1, h_av1, h1,
+                                              heat, cool, c, zred, cosmological)   # :519-526
+            if abs((h_av0 - yh0_av_old) / h_av0) < mfc or h_av0 < mfa:    # :530-535 (temperature_end%current never changes)
+                break
+            if nit > 400:
+                break
+        Tgrid[idx + (2,)] = np.float32(T_end_int)                         # set_temperature_point, :553
+        Tgrid[idx + (1,)] = np.float32(T_end_avg)
+        T_new_avg = float(Tgrid[idx + (1,)])                              # get_temperature_point, :380
+        yh0_prev = 1.0 - max(eps, float(xh_av[idx]))
+        if (abs(h_av0 - yh0_prev) > mfc and abs((h_av0 - yh0_prev) / h_av0) > mfc and h_av0 > mfa) or \
+                (abs((T_start[1] - T_new_avg) / T_new_avg) > 1.0e-1 and abs(T_start[1] - T_new_avg) > 100.0):   # :382-388
+            conv_flag += 1
+        new_int[idx] = h1
+        new_av[idx] = h_av1
+    return conv_flag, new_int, new_av
+
+
+def test_thermal_pass_second_transcription():
+    """isothermal=.false.: one pass over the sources with heating rates, then two per-cell passes with the energy
+    equation, against the C restatement (rates and heating to 1e-10, fractions 1e-12, temperatures as stored floats)"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from problems import make_problem
+    from thermal_common import cooling_table, setup_thermal_oracle
+    tables4 = O.rad_ini_heat()
+    p = make_problem(8, nsrc=3, seed=15, state="random", use_LLS=True, flux=3e8)
+    p["xh"] = 1 - (1 - p["xh"]) * 1e-2
+    c = O.constants()
+    zred = 9.0
+    o = setup_thermal_oracle(p, tables4, zred=zred, cosmological=True)
+    o.xh_av[...] = p["xh"]
+    o.xh_intermed[...] = p["xh"]
+    o.state_before()
+    o.set_rates_to_zero()
+    r = o.pass_all_sources()
+    phih = np.zeros_like(p["xh"])
+    phiheat = np.zeros_like(p["xh"])
+    for ns in (1, 2, 3):
+        res = do_source_py(p, ns, tables4[0], tables4[1], c, heat=(tables4[2], tables4[3]))
+        phih += res[1]
+        phiheat += res[5]
+    np.testing.assert_allclose(o.phih, phih, rtol=1e-10, atol=0)
+    assert np.array_equal(o.phiheat != 0, phiheat != 0)
+    np.testing.assert_allclose(o.phiheat, phiheat, rtol=1e-10, atol=0)
+    lt, lc = cooling_table()
+    cool = (float(lt[0]), float(lt[1] - lt[0]), 10.0 ** lc)              # setup_cool, cooling.f90:77-85
+    dt = 1e6 * c.YEAR
+    Tgrid = o.temperature_grid.copy()
+    for it in range(2):
+        xh_av_in, xh_int_in = o.xh_av.copy(), o.xh_intermed.copy()
+        conv, want_int, want_av = global_pass_thermal_py(p, o.xh.copy(), xh_av_in, xh_int_in, phih, phiheat, Tgrid, dt, c,
+                                                         cool, zred, True)
+        g = o.global_pass(dt, r.photon_loss_all)
+        assert g.conv_flag == conv
+        np.testing.assert_allclose(o.xh_intermed, want_int, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(o.xh_av, want_av, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(o.temperature_grid, Tgrid, rtol=3e-7, atol=0)   # stored as default reals
+    assert float(Tgrid[..., 2].max()) > 1.01e4
