@@ -620,3 +620,64 @@ def test_thermal_pass_second_transcription():
         np.testing.assert_allclose(o.xh_av, want_av, rtol=0, atol=1e-12)
         np.testing.assert_allclose(o.temperature_grid, Tgrid, rtol=3e-7, atol=0)   # stored as default reals
     assert float(Tgrid[..., 2].max()) > 1.01e4
+
+
+def romberg_weights_py(nmax):
+    """romberg_initialisation (romberg.f90:22-90): romw(0:nmax, pmax) for nmax = 2**pmax; the literals -1.0, 4.0 are
+    default reals, so b(k) is formed in single precision before it is stored in real(dp)"""
+    pmax = int(round(math.log(float(nmax)) / math.log(2.0)))
+    f32 = np.float32
+    a, b = [0.0] * (pmax + 1), [0.0] * (pmax + 1)
+    for k in range(1, pmax + 1):
+        b[k] = float(f32(-1.0) / (f32(4.0) ** f32(k) - f32(1.0)))     # :40 (4.0**k is exact in single precision here)
+        a[k] = -b[k] * float(f32(4.0) ** f32(k))                      # :41
+    s = [[0.0] * (pmax + 1) for _ in range(pmax + 1)]
+    romw = [[0.0] * (pmax + 1) for _ in range(nmax + 1)]              # romw[j][i]
+    for k in range(0, pmax + 1):                                      # :53-66
+        s[k][0] = 1.0
+        for j in range(1, pmax + 1):
+            for i in range(pmax, j - 1, -1):
+                s[i][j] = a[j] * s[i][j - 1] + b[j] * s[i - 1][j - 1]
+        for i in range(k, pmax + 1):
+            for j in range(0, 2 ** k + 1):
+                romw[2 ** (i - k) * j][i] = s[i][i] * 2 ** (i - k) + romw[2 ** (i - k) * j][i]
+        s[k][0] = 0.0
+    for i in range(0, pmax + 1):                                      # :70-73
+        romw[0][i] = 0.5 * romw[0][i]
+        romw[2 ** i][i] = 0.5 * romw[2 ** i][i]
+    return [romw[j][pmax] for j in range(nmax + 1)]
+
+
+def test_romberg_weights_and_tables_second_transcription():
+    """the Romberg weights bit for bit, and the photo and heat tables re-integrated in Python from the restatement's SED
+    normalisation: spec_integration / fill_photo_integrands / fill_heating_integrands / make_photo_tables
+    (radiation_tables.F90:130-236, 361-543) with BB_SED (:434-452) and Vector_Romberg (romberg.f90:158-187)"""
+    from c2ray3dm_b200 import constants as K
+    thick, thin, d = O.rad_ini()
+    hthick, hthin = O.rad_ini_heat()[2:]
+    c = O.constants()
+    w = romberg_weights_py(128)
+    assert w == list(d.romw7)
+    nf = 128
+    freq = [d.freq_min + d.delta_freq * float(np.float32(i)) for i in range(nf + 1)]       # :264-272
+    cs = [(f / d.freq_min) ** (-K.pl_index_cross_section_HI) for f in freq]                  # :276-297
+    r2 = d.R_star * d.R_star
+    sed = [4.0 * c.pi * r2 * c.two_pi_over_c_square * f * f / (math.exp(f * d.h_over_kT) - 1.0)
+           if f * d.h_over_kT < 700.0 else 0.0 for f in freq]                                # BB_SED
+    for it in (0, 1, 500, 1000, 1500, 1668, 1700, 1800, 1900, 2000):
+        tau = 0.0 if it == 0 else float(np.float32(10.0)) ** (c.minlogtau + c.dlogtau * float(np.float32(it - 1)))   # :250-256
+        a_thick = a_thin = h_thick = h_thin = 0.0
+        for i in range(nf + 1):
+            if tau * cs[i] < 700.0:
+                f_thick = sed[i] * math.exp(-tau * cs[i])
+                f_thin = sed[i] * cs[i] * math.exp(-tau * cs[i])
+            else:
+                f_thick = f_thin = 0.0
+            a_thick = a_thick + f_thick * d.delta_freq * w[i]
+            a_thin = a_thin + f_thin * d.delta_freq * w[i]
+            h_thick = h_thick + (c.hplanck * (freq[i] - c.ion_freq_HI) * f_thick) * d.delta_freq * w[i]   # :482-487
+            h_thin = h_thin + (c.hplanck * (freq[i] - c.ion_freq_HI) * f_thin) * d.delta_freq * w[i]
+        assert thick[it] == pytest.approx(a_thick, rel=1e-13)
+        assert thin[it] == pytest.approx(a_thin, rel=1e-13)
+        assert hthick[it] == pytest.approx(h_thick, rel=1e-13)
+        assert hthin[it] == pytest.approx(h_thin, rel=1e-13)
